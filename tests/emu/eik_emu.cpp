@@ -1,0 +1,17 @@
+// tests/emu/eik_emu.cpp -- TEST-ONLY host build of the CUDA solver core (csrc/eik_core.cuh).
+// The very same source the GPU kernels instantiate is compiled for the CPU here, with
+// contraction off, so that its FP32 results can be compared with the oracle at scale
+// without a GPU.  Nothing in the product links this file.
+#include "../../mcmc_eq_b200/csrc/eik_core.cuh"
+#include <vector>
+extern "C" int emu_time_2d(const float* s, int nx, int ny, int iz, float* t, int* counters)
+{
+    std::vector<float> tf(eik::kFineMax * 22);
+    eik::Counters c = {};
+    int rc = eik::solve(s, 1, nx, ny, iz, t, tf.data(), 1, counters ? &c : nullptr);
+    if (counters) {
+        counters[0] = c.col_sweeps; counters[1] = c.row_sweeps; counters[2] = c.reverse_sweeps;
+        counters[3] = c.headwaves; counters[4] = c.recursive_init; counters[5] = c.nearest_init; counters[6] = c.box_init;
+    }
+    return rc;
+}
