@@ -1,0 +1,176 @@
+/* mcmceq_b200.h -- C ABI of libmcmceq_b200.so, the B200 implementation of mcmc_eq's
+ * forward-model / likelihood hot path.
+ *
+ * Plain C: pointers and sizes only, every entry point returns an int status
+ * (0 = MQ_OK, negative = error) and never calls exit().  The reference has no FFI;
+ * its seams for this path are four C functions plus the process command line
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it
+ * replaces.  All pointer arguments are HOST pointers unless the name ends in _dev.
+ *
+ * Thread-safety: a handle may be used by one host thread at a time; different handles
+ * (e.g. one per GPU) are independent.  The reference's time_2d keeps file-scope
+ * statics (src/time_2d.c:219-259) and is not re-entrant; this library is.
+ */
+#ifndef MCMCEQ_B200_H
+#define MCMCEQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQ_OK 0
+#define MQ_ERR_ARG (-1)          /* bad argument / size                                          */
+#define MQ_ERR_CUDA (-2)         /* CUDA runtime error, see mq_last_error()                       */
+#define MQ_ERR_UNSUPPORTED (-3)  /* call pattern outside the hot path (see mq_time_2d)            */
+#define MQ_ERR_SOLVER (-4)       /* at least one eikonal solve reported a negative status         */
+#define MQ_ERR_STATCOR (-5)      /* a pick points to an invalid station correction (< -1000);
+                                    the reference prints and exit(0)s, src/misfit.c:93,111         */
+#define MQ_ERR_NOMEM (-6)
+#define MQ_ERR_STATE (-7)        /* call made in the wrong order                                  */
+
+#define MQ_MAX_CLASSES 8         /* 4 pick classes x {P,S}: index = 2*class + (phase == S)        */
+
+/* ---- grid: reference struct GRDHEAD, src/mc.h:91-100 ------------------------------ */
+typedef struct mq_grid {
+    float h;            /* mesh spacing (km)                                    */
+    int32_t nx, ny, nz; /* nodes; the eikonal plane is nxmod x nz,              */
+                        /* nxmod = (int)sqrt(nx*nx+ny*ny)  (src/mcmc_eq.c:520)  */
+    float x0, y0, z0;
+} mq_grid;
+
+/* ---- sampler settings: the 41 lines of config_eqx.dat, src/mcmc_eq.c:345-388 ------ */
+typedef struct mq_config {
+    mq_grid grid;
+    int32_t max_dim;                       /* line 8  */
+    float vpmin, vpmax, vpvsmin, vpvsmax;  /* 9-12    */
+    float noise_min, noise_max;            /* 13-14   */
+    float residual_min, residual_max;      /* 15-16   */
+    float sdevx, sdevy, sdevz;             /* 17-19 (17,18 unused by the reference; 19 = nucleus move) */
+    float sdevvp, sdevvpvs, sdevn;         /* 20-22   */
+    float sdevxs, epi_search;              /* 23      */
+    float sdevys, sdevzs, sdevresidual;    /* 24-26   */
+    float inv_control;                     /* 27, as written in the file (sign = LVZ switch) */
+    int32_t reference_station, scor_flag;  /* 28      */
+    float ref_statcor_P, ref_statcor_S;    /* 28      */
+    int32_t tria;                          /* 29 (only 0 = Voronoi is implemented) */
+    int32_t j_max_start, j_max_main;       /* 30      */
+    int32_t deci;                          /* 31      */
+    int32_t true_random, eikonal;          /* 32      */
+    char dstring_start[64], dstring_main[64]; /* 33   */
+    int32_t aflag;                         /* 34 */
+    char inp_model_switch[16];             /* 34 */
+    float start_vp, sdev_start_vp, start_vp_grad; /* 36 */
+    float start_vpvs, sdev_start_vpvs;     /* 37 */
+    int32_t start_cell_number, sdev_start_cell_number; /* 38 */
+    float start_noise;                     /* 39 */
+    float start_delay, sdev_start_delay;   /* 40 */
+    float r_start_eqh, r_start_eqv;        /* 41 */
+} mq_config;
+
+/* ---- picks: reference struct OBS / struct DATA (src/mc.h:102-134), flattened ------
+ * Picks of event e are [ev_off[e], ev_off[e+1]); inside an event all P picks come first,
+ * then all S picks, each in file order -- the order the reference sums them in
+ * (src/misfit.c:87-119). */
+typedef struct mq_picks {
+    int32_t n_events, n_picks, n_stations;
+    const int32_t* ev_off;   /* [n_events+1]                                        */
+    const int32_t* n_p;      /* [n_events] number of P picks of the event           */
+    const int32_t* st_id;    /* [n_picks]                                           */
+    const float* x;          /* [n_picks] station coordinates (km)                  */
+    const float* y;
+    const float* z;
+    const float* t;          /* [n_picks] observed travel time rel. to reftime (s)  */
+    const int32_t* cls;      /* [n_picks] pick class 0..3                           */
+    const double* reftime;   /* [n_events]                                          */
+    const double* fix;       /* [n_events*3] fixed x,y,z or -9999 (src/mcmc_eq.c:610-612) */
+} mq_picks;
+
+/* ---- chain state: SoA mirror of reference struct Model, src/mc.h:68-89 ------------ */
+typedef struct mq_models {
+    int32_t n_chains, max_dim, n_events, n_stations;
+    int32_t* dim;      /* [n_chains]                      Model.dimension */
+    float* z;          /* [n_chains*max_dim]              Model.z         */
+    float* vp;         /* [n_chains*max_dim]              Model.vp        */
+    float* vpvs;       /* [n_chains*max_dim]              Model.vpvs      */
+    float* eq;         /* [n_chains*n_events*3] x,y,z     Model.eq        */
+    float* pres;       /* [n_chains*n_stations]           Model.pres      */
+    float* sres;       /* [n_chains*n_stations]           Model.sres      */
+    float* noise;      /* [n_chains*8] index 2*class+phase (p_noise0,s_noise0,p_noise1,...) */
+    float* origin;     /* [n_chains*n_events] (output)    Model.origin    */
+} mq_models;
+
+typedef struct mq_handle mq_handle;
+
+const char* mq_version(void);
+/* Text of the last error raised on the calling thread. */
+const char* mq_last_error(void);
+/* Number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches). */
+int64_t mq_launch_count(void);
+
+/* ===== unit-testable twins of the reference functions ================================ */
+
+/* Drop-in for   int time_2d(float*hs,float*t,int nx,int ny,float xs,float ys,float eps,int msg)
+ * (reference src/fdtimes.h:6-7, src/time_2d.c:301).  Same argument meaning and array layout
+ * (x-major, index x*ny+y), one solve on the GPU.  Only the call pattern of the hot path is
+ * implemented: hs constant along x (src/misfit.c:257-266), xs == 0, ys an integer node,
+ * eps_init == 0.001f; anything else returns MQ_ERR_UNSUPPORTED and leaves t untouched.
+ * Unlike the reference, hs is never written to. */
+int mq_time_2d(const float* hs, float* t, int nx, int ny, float xs, float ys, float eps_init, int messages);
+
+/* Batched form: n independent solves on an nxmod x nz plane.  slow[i*nz + k] is h/v of depth
+ * cell k (what src/misfit.c:263 writes into every column of hsbuf), src_iz[i] the source depth
+ * node.  t_out[i] receives the full field in the reference layout (nxmod*nz floats, index
+ * x*nz+y); status[i] (may be NULL) the per-solve code (0 or negative). */
+int mq_eikonal_batch(const float* slow, const int32_t* src_iz, int n, int nxmod, int nz, float* t_out,
+                     int32_t* status, int device);
+
+/* ===== batched sampler ==================================================================
+ * One handle drives n_chains chains on one GPU.  Model state, travel-time tables and RNG
+ * state stay on the device between calls. */
+int mq_create(const mq_config* cfg, const mq_picks* picks, int n_chains, int device, uint64_t seed,
+              mq_handle** out);
+int mq_destroy(mq_handle* h);
+
+/* Upload / download chain states (host SoA <-> device). */
+int mq_set_models(mq_handle* h, const mq_models* m);
+int mq_get_models(mq_handle* h, mq_models* m);
+
+/* Batched drop-in for cal_fit_newx (reference src/misfit.c:45-161) on the models currently in
+ * the handle: calct = 0 none, 1 P tables, 2 S tables, 3 both are rebuilt first
+ * (setup_table_new, src/misfit.c:165-293), then the residual sums of squares per pick class
+ * (mf[chain*8 + 2*class + phase], the reference's *mfp0,*mfs0,*mfp1,...) and the origin times
+ * (origin[chain*n_events + e] = Model.origin) are computed.  mf / origin may be NULL. */
+int mq_forward(mq_handle* h, int calct, float* mf, float* origin);
+
+/* Same, for models passed in host memory: upload, forward, download -- the end-to-end call. */
+int mq_forward_host(mq_handle* h, const mq_models* m, int calct, float* mf, float* origin);
+
+/* Full travel-time table of one chain in the reference layout ttt[nz][nz][nxmod]
+ * (ttt[j][iz][i], src/misfit.c:281-288); phase 1 = P, 2 = S.  Recomputes that chain's table
+ * with every receiver row kept; meant for parity tests and the setup_table_new shim. */
+int mq_get_table(mq_handle* h, int chain, int phase, float* ttt);
+
+/* Per-pick predictions of one chain after mq_forward: what cal_fit_newx prints with out=1
+ * (src/misfit.c:130-143).  resid / tpred are [n_picks] in the handle's pick order. */
+int mq_get_predictions(mq_handle* h, int chain, float* resid, float* tpred);
+
+/* Sampler: random start models (src/mcmc_eq.c:559-630) + first forward (:739-765). */
+int mq_init_chains(mq_handle* h);
+/* n_iters Metropolis-Hastings iterations of every chain (src/mcmc_eq.c:845-1192) with the
+ * device RNG.  proposal_override: NULL = the config's balanced proposal strings
+ * (src/mcmc_eq.c:769-834), else a string of proposal letters to draw from uniformly. */
+int mq_step(mq_handle* h, int n_iters, const char* proposal_override);
+
+/* Per-chain statistics (device -> host). counts[chain*20 + i]: 0 tested(nmod), then a/r pairs
+ * for N,P,V,Q,R,M,B,D in the order of the reference's cnt lines (src/mcmc_eq.c:1199-1207),
+ * 17 accepted, 18 rejected. */
+int mq_get_stats(mq_handle* h, int64_t* counts, double* loglik, double* rms);
+
+int mq_sync(mq_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCMCEQ_B200_H */

@@ -1,0 +1,85 @@
+"""Build the CUDA library (sm_100a) and the CPU checkers in-tree.
+
+`python -m mcmc_eq_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a
+GPU; the resulting .so files are git-ignored but travel to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libmcmceq_b200.so")
+HOST_DIR = os.path.join(PKG, "host")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # keep FP32 products un-fused except where the source says fmaf(): the host build of
+    # the solver core (tests/emu) is then bit-identical to the device code
+    "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def cuda_sources() -> list[str]:
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    srcs = cuda_sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(ROOT, "include", "mcmceq_b200.h"))
+    if not force and _newer(LIB, deps):
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-lcudart"]
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return LIB
+
+
+def build_oracle(force: bool = False) -> None:
+    """Compile oracle/ (our CPU restatement) and, when /root/reference exists, oracle/_ref."""
+    args = ["make", "-C", os.path.join(ROOT, "oracle")]
+    if force:
+        args.append("-B")
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+
+
+def build_emu(force: bool = False) -> str:
+    """Host build of the CUDA solver core, used by the CPU tests only."""
+    src = os.path.join(ROOT, "tests", "emu", "eik_emu.cpp")
+    out = os.path.join(ROOT, "tests", "emu", "libeik_emu.so")
+    deps = [src, os.path.join(CSRC, "eik_core.cuh")]
+    if force or not _newer(out, deps):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused-but-set-variable",
+                        src, "-o", out], check=True)
+    return out
+
+
+def build_host(force: bool = False) -> None:
+    mk = os.path.join(HOST_DIR, "Makefile")
+    if os.path.exists(mk):
+        subprocess.run(["make", "-C", HOST_DIR] + (["-B"] if force else []), check=True, stdout=subprocess.DEVNULL)
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_cuda(force, verbose)
+    build_oracle(force)
+    build_emu(force)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", LIB)

@@ -1,0 +1,42 @@
+// eikonal.cuh -- launch interface of the batched eikonal kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mq {
+
+// One batch of independent solves on an nxmod x nz plane (reference: the nz calls of
+// time_2d in setup_table_new, src/misfit.c:270-289, for many chains and both phases at once).
+struct EikBatch {
+    int nxmod, nz;
+    // Work list.  Either "table mode": n_items slowness columns, every source depth of every
+    // item is solved (n_solves = n_items*nz, solve g -> iz = g / n_items, item = g % n_items,
+    // so that the lanes of a warp share the source depth and with it the sweep schedule), or
+    // "list mode" (src_iz != nullptr): solve g uses column g and source depth src_iz[g].
+    const float* slow;        // [n_items][nz] device, h / v per depth cell
+    int n_items;
+    const int32_t* src_iz;    // [n_solves] device or nullptr
+    int n_solves;
+    // Outputs (device).  full_out: [n_solves][nxmod*nz] in the reference layout (x*nz+y).
+    float* full_out;
+    // Receiver-row tables: table of item i starts at row_out[i] (or row_out_base + i*row_item_stride
+    // when row_out == nullptr) and is laid out [n_rows][nz (source depth)][xpitch].
+    float* const* row_out;
+    float* row_out_base;
+    size_t row_item_stride;
+    const int32_t* rows;      // [n_rows] device: grid rows (receiver layers) that are kept
+    int n_rows, xpitch;
+    int32_t* status;          // [n_solves] device or nullptr
+    // Scratch: per resident warp (nxmod*nz + kFineNodes) * 32 floats.
+    float* scratch;
+    int max_warps;
+};
+
+constexpr int kFineNodes = 22 * 43;   // refined grid of a left-edge source, src/time_2d.c:844-864
+
+size_t eik_scratch_floats_per_warp(int nxmod, int nz);
+// Generic one-lane-per-solve kernel, time field in global memory.
+cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream);
+
+}  // namespace mq
