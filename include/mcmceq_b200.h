@@ -168,6 +168,31 @@ int mq_step(mq_handle* h, int n_iters, const char* proposal_override);
  * 17 accepted, 18 rejected. */
 int mq_get_stats(mq_handle* h, int64_t* counts, double* loglik, double* rms);
 
+/* ---- records: what print_model_raw writes (src/mcmc_eq.c:234-248) ------------------------- */
+#define MQ_REC_MODEL 0    /* decimated accepted model  ("mod", every deci-th accepted, :1163) */
+#define MQ_REC_BEST 1     /* best-RMS model so far     ("bat BF", :1186-1196)                 */
+#define MQ_REC_CURRENT 2  /* current state of the chain ("sta ST" right after mq_init_chains, :763) */
+typedef struct mq_record {
+    int32_t chain, kind;
+    char code;            /* proposal letter that produced the model: Q R P V M B D N ('S' start, 'F' best) */
+    int64_t number;       /* Model.number */
+    int32_t dim;
+    double rms;
+    const float *noise;   /* [8] index 2*class+phase */
+    const float *z, *vp, *vpvs;        /* [dim]           */
+    const float *eq, *origin;          /* [n_events*3], [n_events] */
+    const float *pres, *sres;          /* [n_stations]    */
+} mq_record;
+/* Called once per record; pointers are valid during the call only.  Return non-zero to stop. */
+typedef int (*mq_record_fn)(void* user, const mq_record* rec);
+
+/* Hands every pending decimated record to fn, then clears them.  Each chain holds at most one
+ * pending record, so call this at least every `deci` iterations; *n_lost (may be NULL) counts
+ * records that were overwritten before being drained. */
+int mq_drain(mq_handle* h, mq_record_fn fn, void* user, int* n_lost);
+/* which = 0: current state of `chain`, 1: its best-RMS model so far. */
+int mq_snapshot(mq_handle* h, int chain, int which, mq_record_fn fn, void* user);
+
 int mq_sync(mq_handle* h);
 
 #ifdef __cplusplus

@@ -33,13 +33,17 @@ def _newer(target: str, sources: list[str]) -> bool:
 
 
 def cuda_sources() -> list[str]:
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    # host-side readers/writers of the reference's file formats are part of the same library
+    srcs.append(os.path.join(HOST_DIR, "mq_io.c"))
+    return srcs
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = cuda_sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "mcmceq_b200.h"))
+    deps.append(os.path.join(HOST_DIR, "mq_io.h"))
     if not force and _newer(LIB, deps):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -1,0 +1,844 @@
+// chain.cu -- batched transdimensional Metropolis-Hastings step on the device.
+//
+// Reference: the main loop of mcmc_eq (src/mcmc_eq.c:845-1192): proposal arms Q,R,P,V,M,B,D,N,
+// model_valid (:180-229), rand_* helpers (:122-178), start model (:559-630), acceptance
+// (:1135-1164).  One thread per chain draws the proposal from a counter-based RNG
+// (Philox4x32-10 keyed by seed, indexed by chain and draw number), the forward kernels
+// evaluate all proposals of the iteration at once, one thread per chain decides.
+// Accepting flips buffer indices (model, tables, per-event sums); nothing is copied back
+// and forth the way the reference backs up and restores its travel-time tables.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mcmceq_b200.h"
+#include "chain.cuh"
+#include "errors.h"
+#include "forward.cuh"
+#include "launch_count.h"
+#include "state.h"
+
+namespace mq {
+
+// ---- counter-based RNG ------------------------------------------------------------------
+struct Philox {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t out[4];
+    uint64_t draws;   // number of 32-bit words consumed so far by this chain
+    __device__ void block()
+    {
+        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+    __device__ Philox(uint64_t seed, uint32_t chain, uint64_t draws_)
+    {
+        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+        draws = draws_;
+        ctr[2] = chain; ctr[3] = 0x6d636d63u;
+        set_block(draws >> 2);
+    }
+    __device__ void set_block(uint64_t b) { ctr[0] = (uint32_t)b; ctr[1] = (uint32_t)(b >> 32); block(); }
+    // 31 random bits, the range of libc rand()
+    __device__ uint32_t next31()
+    {
+        const uint32_t w = out[draws & 3];
+        draws++;
+        if ((draws & 3) == 0) set_block(draws >> 2);
+        return w >> 1;
+    }
+    // (float)rand()/RAND_MAX: uniform on [0,1], both ends possible (src/mcmc_eq.c:168-172)
+    __device__ float uniform() { return (float)next31() / 2147483647.0f; }
+    // rand_eq_int (src/mcmc_eq.c:162-166); the reference can return n when rand()==RAND_MAX, clamped here
+    __device__ int below(int n)
+    {
+        const int i = (int)(uniform() * (float)n);
+        return i < n ? i : n - 1;
+    }
+    // rand_eq_limited (src/mcmc_eq.c:174-178)
+    __device__ float between(float lo, float hi) { return lo + (hi - lo) * (float)next31() / 2147483647.0f; }
+    // rand_gauss: polar Box-Muller, second variate discarded (src/mcmc_eq.c:122-135)
+    __device__ float gauss()
+    {
+        float v1, v2, s;
+        do {
+            v1 = 2.0f * uniform() - 1.f;
+            v2 = 2.0f * uniform() - 1.f;
+            s = v1 * v1 + v2 * v2;
+        } while (s >= 1.0f);
+        if (s == 0.0f) return 0.0f;
+        return (float)((double)v1 * sqrt(-2.0 * log((double)s) / (double)s));
+    }
+    // rand_gauss_bounded (src/mcmc_eq.c:149-159): redraw until strictly inside (lo, hi).  The
+    // reference loops for ever when that cannot happen; here the draw gives up (ok = false).
+    __device__ float gauss_bounded(float v0, float sdev, float lo, float hi, bool* ok)
+    {
+        for (int tries = 0; tries < 100000; tries++) {
+            const float dv = gauss() * sdev;
+            if ((v0 + dv) > lo && (v0 + dv) < hi) return dv;
+        }
+        *ok = false;
+        return 0.f;
+    }
+};
+
+struct Snapshot {   // a full copy of a chain's state, for the decimated output and the best model
+    int32_t* dim; float *z, *vp, *vpvs, *eq, *origin, *pres, *sres, *noise;
+    double* rms; int64_t* number; int32_t* code; int32_t* flag;
+};
+
+struct SamplerDev {
+    int64_t *acce, *reject, *counts;
+    uint64_t* draws;
+    float* inv_control;
+    int32_t *kind, *not_valid, *rebuilt;
+    double* log_fac;
+    float* noise_new;
+    double* best_rms;
+    float *wz, *wvp, *wvs;   // model_valid work arrays [n][md]
+    Snapshot out, best;
+    char *ps_start, *ps_main, *ps_over;
+    int len_start, len_main, len_over;
+};
+struct Sampler : SamplerDev {
+    std::string over_host;
+    bool started;
+    SamplerDev dev() const { return *this; }
+};
+
+struct SamplerParams {
+    int n, md, ne, ns, nz;
+    mq_config cfg;
+    float xmin, xmax, ymin, ymax, zmin, zmax;
+    int lvz_flag, revert, sum_of_picks;
+    int n_class[8];
+    uint64_t seed;
+    size_t tab_stride;
+};
+
+static SamplerParams make_params(const Handle* h)
+{
+    SamplerParams p;
+    p.n = h->n; p.md = h->md; p.ne = h->ne; p.ns = h->ns; p.nz = h->nz; p.cfg = h->cfg;
+    p.xmin = h->xmin; p.xmax = h->xmax; p.ymin = h->ymin; p.ymax = h->ymax; p.zmin = h->zmin; p.zmax = h->zmax;
+    p.lvz_flag = h->lvz_flag;
+    p.revert = (int)(h->cfg.j_max_start + h->cfg.j_max_main / 2);   // src/mcmc_eq.c:840
+    p.sum_of_picks = h->sum_of_picks;
+    for (int k = 0; k < 8; k++) p.n_class[k] = h->n_class[k];
+    p.seed = h->seed; p.tab_stride = h->tab_stride;
+    return p;
+}
+
+// ---- model_valid (src/mcmc_eq.c:180-229) on a model in global memory ---------------------
+// Work arrays wz/wp/ws hold the depth-sorted copy.  Returns 0 when valid, 1 otherwise.
+__device__ int model_valid_dev(int dim, const float* z, const float* vp, const float* vpvs, float* wz, float* wp,
+                               float* ws, float dz, float zmin, float zmax, float inv_control)
+{
+    if (dim == 1) return 0;
+    for (int i = 0; i < dim; i++) { wz[i] = z[i]; wp[i] = vp[i]; ws[i] = __fdiv_rn(vp[i], vpvs[i]); }
+    // insertion sort == the reference's bubble sort (both stable, strict > comparisons)
+    for (int i = 1; i < dim; i++) {
+        const float kz = wz[i], kp = wp[i], ks = ws[i];
+        int j = i - 1;
+        while (j >= 0 && wz[j] > kz) { wz[j + 1] = wz[j]; wp[j + 1] = wp[j]; ws[j + 1] = ws[j]; j--; }
+        wz[j + 1] = kz; wp[j + 1] = kp; ws[j + 1] = ks;
+    }
+    float thin = 3.402823466e+38f, prev = zmin;
+    int lvz = 0;
+    for (int i = 0; i < dim; i++) {
+        const float bd = (i < dim - 1) ? (float)((double)__fadd_rn(wz[i], wz[i + 1]) / 2.0) : zmax;
+        const float th = __fsub_rn(bd, prev);
+        if (th < thin) thin = th;
+        prev = bd;
+        if (i < dim - 1) { if (wp[i] > wp[i + 1]) lvz++; if (ws[i] > ws[i + 1]) lvz++; }
+    }
+    if ((double)thin < sqrt((double)__fmul_rn(inv_control, inv_control)) * (double)dz) return 1;
+    if (inv_control < 0.f && lvz > 0) return 1;
+    return 0;
+}
+
+__device__ int find_in_cell_dev(const float* z, int dim, float zq)
+{
+    float best = 3.402823466e+38f;
+    int k = 0;
+    for (int i = 0; i < dim; i++) {
+        const float d = __fsub_rn(z[i], zq), d2 = __fmul_rn(d, d);
+        if (d2 <= best) { best = d2; k = i; }
+    }
+    return k;
+}
+__device__ int find_neighbor_dev(const float* z, int dim, int n)
+{
+    float best = 3.402823466e+38f;
+    int k = 0;
+    for (int i = 0; i < dim; i++) {
+        if (i == n) continue;
+        const float d = __fsub_rn(z[i], z[n]), d2 = __fmul_rn(d, d);
+        if (d2 <= best) { best = d2; k = i; }
+    }
+    return k;
+}
+
+#define MQ_PI 3.141592653   // src/mc.h:50
+
+// ---- start models (src/mcmc_eq.c:549-630) ---------------------------------------------------
+__global__ void init_chains_kernel(SamplerParams p, Handle hd, SamplerDev s)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n) return;
+    const mq_config& g = p.cfg;
+    Philox rng(p.seed, (uint32_t)c, 0);
+    bool ok = true;
+    const float inv = (g.inv_control > 0.f) ? -g.inv_control : g.inv_control;
+    s.inv_control[c] = inv;
+    float* z = hd.z + (size_t)c * p.md;     // buffer 0
+    float* vp = hd.vp + (size_t)c * p.md;
+    float* vpvs = hd.vpvs + (size_t)c * p.md;
+    float* wz = s.wz + (size_t)c * p.md; float* wp = s.wvp + (size_t)c * p.md; float* ws = s.wvs + (size_t)c * p.md;
+    int dim = 1;
+    for (int attempt = 0; attempt < 100000; attempt++) {
+        if (g.start_cell_number > 1)
+            dim = g.start_cell_number + (int)rng.gauss_bounded((float)g.start_cell_number, (float)g.sdev_start_cell_number,
+                                                                1.0f, (float)p.nz, &ok);
+        else dim = 1;
+        if (dim < 1) dim = 1;
+        if (dim > p.md) dim = p.md;
+        for (int i = 0; i < dim; i++) z[i] = rng.between(p.zmin, p.zmax);
+        for (int i = 0; i < dim; i++) {
+            const float value = g.start_vp + (z[i] - g.grid.z0) * g.start_vp_grad;
+            vp[i] = value + rng.gauss_bounded(value, g.sdev_start_vp, g.vpmin, g.vpmax, &ok);
+            vpvs[i] = g.start_vpvs + rng.gauss_bounded(g.start_vpvs, g.sdev_start_vpvs, g.vpvsmin, g.vpvsmax, &ok);
+        }
+        if (model_valid_dev(dim, z, vp, vpvs, wz, wp, ws, g.grid.h, p.zmin, p.zmax, inv) == 0) break;
+    }
+    hd.dim[c] = dim;
+    hd.mcur[c] = 0; hd.tcur[2 * c] = 0; hd.tcur[2 * c + 1] = 0; hd.ecur[c] = 0;
+    float* eq = hd.eq + (size_t)c * p.ne * 3;
+    const float hx = (p.xmax - p.xmin) / 2.0f, hy = (p.ymax - p.ymin) / 2.0f;
+    for (int q = 0; q < p.ne; q++) eq[3 * q] = rng.between(p.xmin + hx * (1.0f - g.r_start_eqh), p.xmin + hx * (1.0f + g.r_start_eqh));
+    for (int q = 0; q < p.ne; q++) eq[3 * q + 1] = rng.between(p.ymin + hy * (1.0f - g.r_start_eqh), p.ymin + hy * (1.0f + g.r_start_eqh));
+    for (int q = 0; q < p.ne; q++) eq[3 * q + 2] = rng.between(p.zmin, p.zmax * g.r_start_eqv);
+    for (int q = 0; q < p.ne; q++)
+        for (int k = 0; k < 3; k++)
+            if (hd.pk.fix[3 * q + k] != -9999.0) eq[3 * q + k] = (float)hd.pk.fix[3 * q + k];
+    float* pres = hd.pres + (size_t)c * p.ns;
+    float* sres = hd.sres + (size_t)c * p.ns;
+    for (int i = 0; i < p.ns; i++) pres[i] = g.start_delay + rng.gauss_bounded(g.start_delay, g.sdev_start_delay, g.residual_min, g.residual_max, &ok);
+    for (int i = 0; i < p.ns; i++) sres[i] = g.start_delay + rng.gauss_bounded(g.start_delay, g.sdev_start_delay, g.residual_min, g.residual_max, &ok);
+    if (g.scor_flag == 1 || g.scor_flag == 2) pres[g.reference_station] = g.ref_statcor_P;
+    if (g.scor_flag == 2) sres[g.reference_station] = g.ref_statcor_S;
+    for (int k = 0; k < 8; k++) hd.noise[8 * (size_t)c + k] = g.start_noise;
+    s.draws[c] = rng.draws;
+    s.acce[c] = 0; s.reject[c] = 0;
+    for (int k = 0; k < 20; k++) s.counts[20 * (size_t)c + k] = 0;
+    if (!ok) atomicExch(hd.err, MQ_ERR_ARG);
+}
+
+// ---- proposal (src/mcmc_eq.c:856-1130) --------------------------------------------------------
+__global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView v, int use_override)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n) return;
+    const mq_config& g = p.cfg;
+    const int n = p.n;
+    // default: nothing to evaluate
+    v.q_idx[c] = -1; v.r_idx[c] = -1; v.ev_only[c] = -2;
+    const int mc = hd.mcur[c], ec = hd.ecur[c];
+    v.mbuf[c] = mc; v.tbuf[2 * c] = hd.tcur[2 * c]; v.tbuf[2 * c + 1] = hd.tcur[2 * c + 1]; v.ebuf[c] = ec;
+    s.kind[c] = 0; s.not_valid[c] = 0; s.rebuilt[c] = 0; s.log_fac[c] = 0.0;
+
+    const long j = (long)s.acce[c];
+    if (j >= (long)g.j_max_start + (long)g.j_max_main) return;   // chain finished (src/mcmc_eq.c:845)
+
+    Philox rng(p.seed, (uint32_t)c, s.draws[c]);
+    float inv = s.inv_control[c];
+    if (j == p.revert && p.lvz_flag == 1) { inv = -inv; s.inv_control[c] = inv; }   // fires every iteration while acce == revert (:849-853)
+
+    char kind;
+    float fac;
+    if (use_override) { kind = s.ps_over[rng.below(s.len_over)]; fac = (j <= g.j_max_start) ? g.epi_search : 1.0f; }
+    else if (j <= g.j_max_start) { kind = s.ps_start[rng.below(s.len_start)]; fac = g.epi_search; }
+    else { kind = s.ps_main[rng.below(s.len_main)]; fac = 1.0f; }
+    s.kind[c] = kind;
+
+    const int dim = hd.dim[mc * n + c];
+    const float* z = hd.z + ((size_t)mc * n + c) * p.md;
+    const float* vp = hd.vp + ((size_t)mc * n + c) * p.md;
+    const float* vpvs = hd.vpvs + ((size_t)mc * n + c) * p.md;
+    const int mo = 1 - mc;
+    float* nz_ = hd.z + ((size_t)mo * n + c) * p.md;
+    float* nvp = hd.vp + ((size_t)mo * n + c) * p.md;
+    float* nvpvs = hd.vpvs + ((size_t)mo * n + c) * p.md;
+    float* wz = s.wz + (size_t)c * p.md; float* wp = s.wvp + (size_t)c * p.md; float* ws = s.wvs + (size_t)c * p.md;
+    bool ok = true;
+    int calct = 0, newdim = dim;
+    bool model_arm = false;
+    const int kMaxTries = 100000;
+
+    switch (kind) {
+    case 'Q': {
+        const int idx = rng.below(p.ne);
+        const float* q = hd.eq + ((size_t)c * p.ne + idx) * 3;
+        float dx = rng.gauss_bounded(q[0], g.sdevxs * fac, p.xmin, p.xmax, &ok);
+        float dy = rng.gauss_bounded(q[1], g.sdevys * fac, p.ymin, p.ymax, &ok);
+        float dz = rng.gauss_bounded(q[2], g.sdevzs * fac, p.zmin, p.zmax, &ok);
+        if (hd.pk.fix[3 * idx] != -9999.0) dx = 0.f;
+        if (hd.pk.fix[3 * idx + 1] != -9999.0) dy = 0.f;
+        if (hd.pk.fix[3 * idx + 2] != -9999.0) dz = 0.f;
+        v.q_idx[c] = idx;
+        v.q_xyz[3 * c] = q[0] + dx; v.q_xyz[3 * c + 1] = q[1] + dy; v.q_xyz[3 * c + 2] = q[2] + dz;
+        v.ev_only[c] = idx;
+        break;
+    }
+    case 'R': {
+        const int idx = rng.below(p.ns);
+        float dx = rng.gauss_bounded(hd.pres[(size_t)c * p.ns + idx], g.sdevresidual, g.residual_min, g.residual_max, &ok);
+        float dy = rng.gauss_bounded(hd.sres[(size_t)c * p.ns + idx], g.sdevresidual, g.residual_min, g.residual_max, &ok);
+        if (g.scor_flag == -1) dy = 0.f;
+        if (g.scor_flag == -2) dx = 0.f;
+        float dx2 = 0.f, dy2 = 0.f;
+        if (g.scor_flag != 0) {   // second addition of the reference (:919-928); for flags -1/-2 dx is applied twice
+            dx2 = dx; dy2 = dy;
+            if (g.reference_station == idx) {
+                if (g.scor_flag == 1) dx2 = 0.f;
+                if (g.scor_flag == 2) { dx2 = 0.f; dy2 = 0.f; }
+            }
+        }
+        v.r_idx[c] = idx;
+        v.r_d[4 * c] = dx; v.r_d[4 * c + 1] = dy; v.r_d[4 * c + 2] = dx2; v.r_d[4 * c + 3] = dy2;
+        v.ev_only[c] = -1; v.ebuf[c] = 1 - ec;
+        break;
+    }
+    case 'P': case 'V': case 'M': {
+        if (kind == 'M' && !(dim > 1)) { s.not_valid[c] = 1; break; }
+        int t;
+        for (t = 0; t < kMaxTries; t++) {
+            for (int i = 0; i < dim; i++) { nz_[i] = z[i]; nvp[i] = vp[i]; nvpvs[i] = vpvs[i]; }
+            const int idx = rng.below(dim);
+            if (kind == 'P') nvp[idx] = vp[idx] + rng.gauss_bounded(vp[idx], g.sdevvp, g.vpmin, g.vpmax, &ok);
+            else if (kind == 'V') nvpvs[idx] = vpvs[idx] + rng.gauss_bounded(vpvs[idx], g.sdevvpvs, g.vpvsmin, g.vpvsmax, &ok);
+            else nz_[idx] = z[idx] + rng.gauss_bounded(z[idx], g.sdevz, p.zmin, p.zmax, &ok);
+            if (model_valid_dev(dim, nz_, nvp, nvpvs, wz, wp, ws, g.grid.h, p.zmin, p.zmax, inv) == 0) break;
+        }
+        if (t == kMaxTries) ok = false;
+        calct = (kind == 'V') ? 2 : 3;
+        model_arm = true;
+        break;
+    }
+    case 'B': {
+        if (!((double)(dim + 1) < ((double)g.max_dim / (1.0 + sqrt((double)(inv * inv))))) || dim + 1 > p.md) { s.not_valid[c] = 1; break; }
+        int t, idx = 0;
+        for (t = 0; t < kMaxTries; t++) {
+            for (int i = 0; i < dim; i++) { nz_[i] = z[i]; nvp[i] = vp[i]; nvpvs[i] = vpvs[i]; }
+            const float newz = rng.between(p.zmin, p.zmax);
+            idx = find_in_cell_dev(z, dim, newz);
+            const float dvp = rng.gauss_bounded(vp[idx], g.sdevvp, g.vpmin, g.vpmax, &ok);
+            const float dvs = rng.gauss_bounded(vpvs[idx], g.sdevvpvs, g.vpvsmin, g.vpvsmax, &ok);
+            nvp[dim] = vp[idx] + dvp; nvpvs[dim] = vpvs[idx] + dvs; nz_[dim] = newz;
+            if (model_valid_dev(dim + 1, nz_, nvp, nvpvs, wz, wp, ws, g.grid.h, p.zmin, p.zmax, inv) == 0) break;
+        }
+        if (t == kMaxTries) ok = false;
+        newdim = dim + 1;
+        {
+            const float dv = nvp[dim] - nvp[idx], ds = nvpvs[dim] - nvpvs[idx];
+            double lf = log((double)g.sdevvp * sqrt(2.0 * MQ_PI) / (double)(g.vpmax - g.vpmin)) +
+                        (double)(dv * dv) / 2.0 / (double)g.sdevvp / (double)g.sdevvp;
+            if (g.sdevvpvs != 0.f)
+                lf = lf + log((double)g.sdevvpvs * sqrt(2.0 * MQ_PI) / (double)(g.vpvsmax - g.vpvsmin)) +
+                     (double)(ds * ds) / 2.0 / (double)g.sdevvpvs / (double)g.sdevvpvs;
+            s.log_fac[c] = lf;
+        }
+        calct = 3; model_arm = true;
+        break;
+    }
+    case 'D': {
+        if (!(dim > 1)) { s.not_valid[c] = 1; break; }
+        int t;
+        double lf = 0.0;
+        for (t = 0; t < kMaxTries; t++) {
+            const int dead = rng.below(dim);
+            const int nb = find_neighbor_dev(z, dim, dead);
+            const float dv = vp[dead] - vp[nb], ds = vpvs[dead] - vpvs[nb];
+            lf = log((double)((g.vpmax - g.vpmin) / g.sdevvp) / sqrt(2.0 * MQ_PI)) -
+                 (double)(dv * dv) / 2.0 / (double)g.sdevvp / (double)g.sdevvp;
+            if (g.sdevvpvs != 0.f)
+                lf = lf + log((double)((g.vpvsmax - g.vpvsmin) / g.sdevvpvs) / sqrt(2.0 * MQ_PI)) -
+                     (double)(ds * ds) / 2.0 / (double)g.sdevvpvs / (double)g.sdevvpvs;
+            for (int i = 0, k = 0; i < dim; i++) if (i != dead) { nz_[k] = z[i]; nvp[k] = vp[i]; nvpvs[k] = vpvs[i]; k++; }
+            if (model_valid_dev(dim - 1, nz_, nvp, nvpvs, wz, wp, ws, g.grid.h, p.zmin, p.zmax, inv) == 0) break;
+        }
+        if (t == kMaxTries) ok = false;
+        newdim = dim - 1;
+        s.log_fac[c] = lf;
+        calct = 3; model_arm = true;
+        break;
+    }
+    case 'N': {
+        const float* o = hd.noise + 8 * (size_t)c;
+        float* nn = s.noise_new + 8 * (size_t)c;
+        double lf = 0.0;
+        // draw order p0,s0,p1,s1,... == index order 2*class+phase (:1097-1112)
+        for (int k = 0; k < 8; k++) nn[k] = o[k] + rng.gauss_bounded(o[k], g.sdevn, g.noise_min, g.noise_max, &ok);
+        for (int k = 0; k < 8; k++) lf = lf + (double)p.n_class[k] * log((double)(o[k] / nn[k]));
+        s.log_fac[c] = lf;
+        v.ev_only[c] = -2;
+        break;
+    }
+    default: s.not_valid[c] = 1; break;
+    }
+
+    if (model_arm) {
+        hd.dim[mo * n + c] = newdim;
+        v.mbuf[c] = mo;
+        v.ev_only[c] = -1; v.ebuf[c] = 1 - ec;
+        s.rebuilt[c] = calct;
+        if (p.cfg.eikonal == 1 && p.cfg.aflag != 1) {
+            for (int ph = 0; ph < 2; ph++) {
+                if (!(calct & (1 << ph))) continue;
+                const int tb = 1 - hd.tcur[2 * c + ph];
+                v.tbuf[2 * c + ph] = tb;
+                const int item = atomicAdd(hd.n_items, 1);
+                hd.item_chain[item] = c; hd.item_phase[item] = ph;
+                hd.item_tab[item] = hd.tab + (((size_t)tb * n + c) * 2 + ph) * p.tab_stride;
+            }
+        }
+    }
+    if (p.cfg.aflag == 1) v.ev_only[c] = -2;   // prior sampling: no likelihood (src/misfit.c:61)
+    if (!ok) { s.not_valid[c] = 1; v.ev_only[c] = -2; }
+    s.draws[c] = rng.draws;
+}
+
+// ---- accept / reject (src/mcmc_eq.c:1135-1191) -------------------------------------------------
+__global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView v)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n) return;
+    const char kind = (char)s.kind[c];
+    if (kind == 0) return;   // finished chain
+    const mq_config& g = p.cfg;
+    const int n = p.n;
+    int64_t* cnt = s.counts + 20 * (size_t)c;
+    const int slot = (kind == 'N') ? 0 : (kind == 'P') ? 1 : (kind == 'V') ? 2 : (kind == 'Q') ? 3 : (kind == 'R') ? 4
+                   : (kind == 'M') ? 5 : (kind == 'B') ? 6 : 7;
+    const int not_valid = s.not_valid[c];
+    float mf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* noise = (kind == 'N') ? s.noise_new + 8 * (size_t)c : hd.noise + 8 * (size_t)c;
+    float alpha;
+    double new_misfit = 0, new_rms = 0, new_ll = 0;
+    if (not_valid) {
+        alpha = 0.f;   // ineligible move: still consumes a uniform and counts as a rejection (quirk Q5)
+    } else {
+        for (int k = 0; k < 8; k++) mf[k] = (g.aflag == 1) ? 0.f : hd.mf_eval[8 * (size_t)c + k];
+        new_misfit = chain_misfit(mf, noise);
+        new_rms = chain_rms(mf, p.sum_of_picks);
+        new_ll = -new_misfit / 2.0;
+        alpha = chain_alpha(s.log_fac[c], new_ll, hd.ll[c]);
+        cnt[0]++;   // nmod: models whose misfit was evaluated
+    }
+    if (g.aflag == 1) alpha = 1.f;
+    if (not_valid && g.aflag == 0) alpha = 0.f;
+
+    Philox rng(p.seed, (uint32_t)c, s.draws[c]);
+    const float u = rng.uniform();
+    s.draws[c] = rng.draws;
+
+    if (u < alpha) {
+        const int64_t number = s.acce[c];
+        s.acce[c] = number + 1;
+        cnt[1 + 2 * slot]++;
+        cnt[17]++;
+        // apply the proposal
+        if (kind == 'Q') {
+            const int idx = v.q_idx[c];
+            float* q = hd.eq + ((size_t)c * p.ne + idx) * 3;
+            q[0] = v.q_xyz[3 * c]; q[1] = v.q_xyz[3 * c + 1]; q[2] = v.q_xyz[3 * c + 2];
+            if (g.aflag != 1) {
+                const int ec = hd.ecur[c];
+                float* es = hd.evsum + (((size_t)ec * n + c) * p.ne + idx) * 8;
+                for (int k = 0; k < 8; k++) es[k] = hd.evq[8 * (size_t)c + k];
+                hd.origin[((size_t)ec * n + c) * p.ne + idx] = hd.oq[c];
+            }
+        } else if (kind == 'R') {
+            const int idx = v.r_idx[c];
+            const float dx = v.r_d[4 * c], dy = v.r_d[4 * c + 1], dx2 = v.r_d[4 * c + 2], dy2 = v.r_d[4 * c + 3];
+            float* pres = hd.pres + (size_t)c * p.ns;
+            float* sres = hd.sres + (size_t)c * p.ns;
+            const float nsm1 = (float)(p.ns - 1);
+            if (g.scor_flag <= 0)
+                for (int k = 0; k < p.ns; k++) {
+                    pres[k] = (k == idx) ? __fadd_rn(pres[k], dx) : __fsub_rn(pres[k], __fdiv_rn(dx, nsm1));
+                    sres[k] = (k == idx) ? __fadd_rn(sres[k], dy) : __fsub_rn(sres[k], __fdiv_rn(dy, nsm1));
+                }
+            if (g.scor_flag != 0) { pres[idx] = __fadd_rn(pres[idx], dx2); sres[idx] = __fadd_rn(sres[idx], dy2); }
+            if (g.aflag != 1) hd.ecur[c] = v.ebuf[c];
+        } else if (kind == 'N') {
+            for (int k = 0; k < 8; k++) hd.noise[8 * (size_t)c + k] = noise[k];
+        } else {   // P V M B D
+            hd.mcur[c] = v.mbuf[c];
+            hd.tcur[2 * c] = v.tbuf[2 * c];
+            hd.tcur[2 * c + 1] = v.tbuf[2 * c + 1];
+            if (g.aflag != 1) hd.ecur[c] = v.ebuf[c];
+        }
+        {
+            for (int k = 0; k < 8; k++) hd.mf[8 * (size_t)c + k] = mf[k];
+            hd.ll[c] = new_ll; hd.rms[c] = new_rms; hd.misfit[c] = new_misfit;
+        }
+        // decimated output (src/mcmc_eq.c:1163) and best model (src/mcmc_eq.c:1186-1191)
+        const int64_t acce = number + 1;
+        if (g.deci > 0 && (acce / g.deci) * g.deci == acce) {
+            if (s.out.flag[c]) s.out.flag[c] = 3;   // previous record not drained yet: it is overwritten
+            else s.out.flag[c] = 2;                 // 2/3 = snapshot requested
+            s.out.number[c] = number; s.out.code[c] = kind; s.out.rms[c] = new_rms;
+        }
+        if (new_rms < s.best_rms[c]) { s.best_rms[c] = new_rms; s.best.flag[c] = 2; s.best.number[c] = number; s.best.rms[c] = new_rms; }
+    } else {
+        s.reject[c]++;
+        cnt[2 + 2 * slot]++;
+        cnt[18]++;
+    }
+}
+
+// ---- snapshots: one block per chain copies the current state when asked to ----------------------
+__device__ void snapshot_copy(const SamplerParams& p, const Handle& hd, const Snapshot& d, int c)
+{
+    const int n = p.n, mc = hd.mcur[c], ec = hd.ecur[c];
+    const int dim = hd.dim[mc * n + c];
+    const size_t mo = ((size_t)mc * n + c) * p.md;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        d.z[(size_t)c * p.md + i] = hd.z[mo + i]; d.vp[(size_t)c * p.md + i] = hd.vp[mo + i]; d.vpvs[(size_t)c * p.md + i] = hd.vpvs[mo + i];
+    }
+    for (int i = threadIdx.x; i < 3 * p.ne; i += blockDim.x) d.eq[(size_t)c * p.ne * 3 + i] = hd.eq[(size_t)c * p.ne * 3 + i];
+    for (int i = threadIdx.x; i < p.ne; i += blockDim.x) d.origin[(size_t)c * p.ne + i] = hd.origin[((size_t)ec * n + c) * p.ne + i];
+    for (int i = threadIdx.x; i < p.ns; i += blockDim.x) { d.pres[(size_t)c * p.ns + i] = hd.pres[(size_t)c * p.ns + i]; d.sres[(size_t)c * p.ns + i] = hd.sres[(size_t)c * p.ns + i]; }
+    if (threadIdx.x < 8) d.noise[8 * (size_t)c + threadIdx.x] = hd.noise[8 * (size_t)c + threadIdx.x];
+    if (threadIdx.x == 0) d.dim[c] = dim;
+}
+
+__global__ void snapshot_kernel(SamplerParams p, Handle hd, SamplerDev s)
+{
+    const int c = blockIdx.x;
+    if (s.out.flag[c] >= 2) {
+        snapshot_copy(p, hd, s.out, c);
+        __syncthreads();
+        if (threadIdx.x == 0) s.out.flag[c] = 1;   // 1 = ready for mq_drain
+    }
+    if (s.best.flag[c] >= 2) {
+        snapshot_copy(p, hd, s.best, c);
+        __syncthreads();
+        if (threadIdx.x == 0) s.best.flag[c] = 1;
+    }
+}
+
+__global__ void init_best_kernel(int n, const double* rms, SamplerDev s)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    s.best_rms[c] = rms[c];
+    s.best.flag[c] = 2; s.best.number[c] = 0; s.best.rms[c] = rms[c];
+    s.out.flag[c] = 0;
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+template <class T>
+static cudaError_t dz(T** p, size_t count)
+{
+    cudaError_t e = cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, (count ? count : 1) * sizeof(T));
+    return e;
+}
+
+static cudaError_t alloc_snapshot(Snapshot* d, const Handle* h)
+{
+    const size_t n = h->n;
+    cudaError_t e;
+    if ((e = dz(&d->dim, n))) return e;
+    if ((e = dz(&d->z, n * h->md))) return e;
+    if ((e = dz(&d->vp, n * h->md))) return e;
+    if ((e = dz(&d->vpvs, n * h->md))) return e;
+    if ((e = dz(&d->eq, n * h->ne * 3))) return e;
+    if ((e = dz(&d->origin, n * h->ne))) return e;
+    if ((e = dz(&d->pres, n * h->ns))) return e;
+    if ((e = dz(&d->sres, n * h->ns))) return e;
+    if ((e = dz(&d->noise, n * 8))) return e;
+    if ((e = dz(&d->rms, n))) return e;
+    if ((e = dz(&d->number, n))) return e;
+    if ((e = dz(&d->code, n))) return e;
+    if ((e = dz(&d->flag, n))) return e;
+    return cudaSuccess;
+}
+static void free_snapshot(Snapshot* d)
+{
+    cudaFree(d->dim); cudaFree(d->z); cudaFree(d->vp); cudaFree(d->vpvs); cudaFree(d->eq); cudaFree(d->origin);
+    cudaFree(d->pres); cudaFree(d->sres); cudaFree(d->noise); cudaFree(d->rms); cudaFree(d->number); cudaFree(d->code); cudaFree(d->flag);
+}
+
+// Balanced proposal strings (src/mcmc_eq.c:769-834): Q and R are repeated once per `per` events / stations.
+static std::string balance(const char* letters, int noq, int nos, int per)
+{
+    std::string out;
+    for (const char* q = letters; *q; q++) {
+        switch (*q) {
+        case 'Q': for (int j = 0; j < noq; j += per) out += 'Q'; break;
+        case 'R': for (int j = 0; j < nos; j += per) out += 'R'; break;
+        case 'N': case 'M': case 'V': case 'P': case 'B': case 'D': out += *q; break;
+        default: break;
+        }
+    }
+    return out;
+}
+
+static cudaError_t upload_string(char** d, const std::string& s)
+{
+    cudaFree(*d);
+    *d = nullptr;
+    cudaError_t e = cudaMalloc((void**)d, s.size() + 1);
+    if (e == cudaSuccess) e = cudaMemcpy(*d, s.c_str(), s.size() + 1, cudaMemcpyHostToDevice);
+    return e;
+}
+
+static int sampler_get(Handle* h, Sampler** out)
+{
+    if (h->sampler) { *out = (Sampler*)h->sampler; return MQ_OK; }
+    Sampler* s = new Sampler();
+    memset((void*)static_cast<SamplerDev*>(s), 0, sizeof(SamplerDev));
+    s->started = false;
+    const size_t n = h->n;
+#define TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(e_)); return MQ_ERR_CUDA; } } while (0)
+    TRY(dz(&s->acce, n)); TRY(dz(&s->reject, n)); TRY(dz(&s->counts, n * 20)); TRY(dz(&s->draws, n));
+    TRY(dz(&s->inv_control, n)); TRY(dz(&s->kind, n)); TRY(dz(&s->not_valid, n)); TRY(dz(&s->rebuilt, n));
+    TRY(dz(&s->log_fac, n)); TRY(dz(&s->noise_new, n * 8)); TRY(dz(&s->best_rms, n));
+    TRY(dz(&s->wz, n * h->md)); TRY(dz(&s->wvp, n * h->md)); TRY(dz(&s->wvs, n * h->md));
+    TRY(alloc_snapshot(&s->out, h)); TRY(alloc_snapshot(&s->best, h));
+    const std::string a = balance(h->cfg.dstring_start, h->ne, h->ns, 10), b = balance(h->cfg.dstring_main, h->ne, h->ns, 20);
+    s->len_start = (int)a.size(); s->len_main = (int)b.size();
+    TRY(upload_string(&s->ps_start, a)); TRY(upload_string(&s->ps_main, b));
+    {
+        std::vector<float> inv(n, h->inv_control);
+        TRY(cudaMemcpy(s->inv_control, inv.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+#undef TRY
+    h->sampler = s;
+    *out = s;
+    return MQ_OK;
+}
+
+void sampler_destroy(Handle* h)
+{
+    Sampler* s = (Sampler*)h->sampler;
+    if (!s) return;
+    cudaFree(s->acce); cudaFree(s->reject); cudaFree(s->counts); cudaFree(s->draws); cudaFree(s->inv_control);
+    cudaFree(s->kind); cudaFree(s->not_valid); cudaFree(s->rebuilt); cudaFree(s->log_fac); cudaFree(s->noise_new);
+    cudaFree(s->best_rms); cudaFree(s->wz); cudaFree(s->wvp); cudaFree(s->wvs);
+    free_snapshot(&s->out); free_snapshot(&s->best);
+    cudaFree(s->ps_start); cudaFree(s->ps_main); cudaFree(s->ps_over);
+    delete s;
+    h->sampler = nullptr;
+}
+
+}  // namespace mq
+
+using namespace mq;
+
+static int start_sampler_state(Handle* h, Sampler* s)
+{
+    // first forward of the start models and the "best so far" bookkeeping (src/mcmc_eq.c:739-765)
+    int rc = forward_current_device(h, 3);
+    if (rc != MQ_OK) return rc;
+    init_best_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->n, h->rms, s->dev());
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    const SamplerParams p = make_params(h);
+    snapshot_kernel<<<h->n, 128, 0, h->stream>>>(p, *h, s->dev());
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    MQ_CUDA(cudaStreamSynchronize(h->stream));
+    s->started = true;
+    return MQ_OK;
+}
+
+extern "C" int mq_init_chains(mq_handle* hh)
+{
+    if (!hh) { set_error("mq_init_chains: null"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    MQ_CUDA(cudaSetDevice(h->device));
+    Sampler* s;
+    int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    const SamplerParams p = make_params(h);
+    if (s->len_start < 1 || s->len_main < 1) { set_error("mq_init_chains: empty proposal string (config line 33)"); return MQ_ERR_ARG; }
+    init_chains_kernel<<<(h->n + 63) / 64, 64, 0, h->stream>>>(p, *h, s->dev());
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    h->models_set = true;
+    return start_sampler_state(h, s);
+}
+
+extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override)
+{
+    if (!hh || n_iters < 0) { set_error("mq_step: bad argument"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    if (!h->models_set) { set_error("mq_step: no models (mq_init_chains or mq_set_models first)"); return MQ_ERR_STATE; }
+    MQ_CUDA(cudaSetDevice(h->device));
+    Sampler* s;
+    int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    if (!s->started || !h->forward_done) {   // chains supplied through mq_set_models
+        rc = start_sampler_state(h, s);
+        if (rc != MQ_OK) return rc;
+    }
+    int use_override = 0;
+    if (proposal_override && *proposal_override) {
+        for (const char* q = proposal_override; *q; q++)
+            if (!strchr("QRPVMBDN", *q)) { set_error("mq_step: unknown proposal letter '%c'", *q); return MQ_ERR_ARG; }
+        if (s->over_host != proposal_override) {
+            s->over_host = proposal_override;
+            s->len_over = (int)s->over_host.size();
+            MQ_CUDA(upload_string(&s->ps_over, s->over_host));
+        }
+        use_override = 1;
+    }
+    const SamplerParams p = make_params(h);
+    cudaStream_t st = h->stream;
+    const int grid = (h->n + 63) / 64;
+    for (int it = 0; it < n_iters; it++) {
+        MQ_CUDA(cudaMemsetAsync(h->n_items, 0, sizeof(int32_t), st));
+        propose_kernel<<<grid, 64, 0, st>>>(p, *h, s->dev(), h->prop_view, use_override);
+        count_launch();
+        MQ_CUDA(cudaGetLastError());
+        if (h->cfg.aflag != 1) {
+            if (h->cfg.eikonal == 1) {
+                MQ_CUDA(launch_rasterise(h, h->prop_view, 2 * h->n));
+                MQ_CUDA(launch_tables(h, 2 * h->n));
+            }
+            MQ_CUDA(launch_misfit(h, h->prop_view));
+            MQ_CUDA(launch_totals(h, h->prop_view));
+        }
+        accept_kernel<<<grid, 64, 0, st>>>(p, *h, s->dev(), h->prop_view);
+        count_launch();
+        MQ_CUDA(cudaGetLastError());
+        snapshot_kernel<<<h->n, 128, 0, st>>>(p, *h, s->dev());
+        count_launch();
+        MQ_CUDA(cudaGetLastError());
+    }
+    return MQ_OK;
+}
+
+extern "C" int mq_get_stats(mq_handle* hh, int64_t* counts, double* loglik, double* rms)
+{
+    if (!hh) { set_error("mq_get_stats: null"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    MQ_CUDA(cudaSetDevice(h->device));
+    Sampler* s;
+    int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    const size_t n = h->n;
+    if (counts) MQ_CUDA(cudaMemcpyAsync(counts, s->counts, n * 20 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (loglik) MQ_CUDA(cudaMemcpyAsync(loglik, h->ll, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (rms) MQ_CUDA(cudaMemcpyAsync(rms, h->rms, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MQ_CUDA(cudaStreamSynchronize(h->stream));
+    return MQ_OK;
+}
+
+// ---- records ---------------------------------------------------------------------------------
+static int fetch_snapshot(Handle* h, const Snapshot& d, int c, std::vector<float>& buf, mq_record* r)
+{
+    const size_t md = h->md, ne = h->ne, ns = h->ns;
+    buf.resize(3 * md + 4 * ne + 2 * ns + 8);
+    float* z = buf.data(); float* vp = z + md; float* vpvs = vp + md; float* eq = vpvs + md; float* origin = eq + 3 * ne;
+    float* pres = origin + ne; float* sres = pres + ns; float* noise = sres + ns;
+    int32_t dim = 0, code = 0;
+    cudaStream_t st = h->stream;
+#define D2H(dst, src, cnt) MQ_CUDA(cudaMemcpyAsync(dst, src, (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st))
+    D2H(&dim, d.dim + c, 1); D2H(&code, d.code + c, 1); D2H(&r->number, d.number + c, 1); D2H(&r->rms, d.rms + c, 1);
+    D2H(z, d.z + c * md, md); D2H(vp, d.vp + c * md, md); D2H(vpvs, d.vpvs + c * md, md);
+    D2H(eq, d.eq + c * ne * 3, 3 * ne); D2H(origin, d.origin + c * ne, ne);
+    D2H(pres, d.pres + c * ns, ns); D2H(sres, d.sres + c * ns, ns); D2H(noise, d.noise + 8 * (size_t)c, 8);
+#undef D2H
+    MQ_CUDA(cudaStreamSynchronize(st));
+    r->chain = c; r->dim = dim; r->code = (char)code;
+    r->z = z; r->vp = vp; r->vpvs = vpvs; r->eq = eq; r->origin = origin; r->pres = pres; r->sres = sres; r->noise = noise;
+    return MQ_OK;
+}
+
+extern "C" int mq_drain(mq_handle* hh, mq_record_fn fn, void* user, int* n_lost)
+{
+    if (!hh || !fn) { set_error("mq_drain: null"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    MQ_CUDA(cudaSetDevice(h->device));
+    Sampler* s;
+    int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    std::vector<int32_t> flag(h->n);
+    MQ_CUDA(cudaMemcpyAsync(flag.data(), s->out.flag, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    MQ_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<float> buf;
+    int lost = 0;
+    for (int c = 0; c < h->n; c++) {
+        if (!flag[c]) continue;
+        mq_record r;
+        memset(&r, 0, sizeof r);
+        rc = fetch_snapshot(h, s->out, c, buf, &r);
+        if (rc != MQ_OK) return rc;
+        r.kind = MQ_REC_MODEL;
+        if (flag[c] == 3) lost++;
+        const int stop = fn(user, &r);
+        if (stop) break;
+    }
+    MQ_CUDA(cudaMemsetAsync(s->out.flag, 0, h->n * sizeof(int32_t), h->stream));
+    MQ_CUDA(cudaStreamSynchronize(h->stream));
+    if (n_lost) *n_lost = lost;
+    return MQ_OK;
+}
+
+extern "C" int mq_snapshot(mq_handle* hh, int chain, int which, mq_record_fn fn, void* user)
+{
+    if (!hh || !fn || chain < 0 || chain >= hh->h.n || which < 0 || which > 1) { set_error("mq_snapshot: bad argument"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    MQ_CUDA(cudaSetDevice(h->device));
+    Sampler* s;
+    int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    std::vector<float> buf;
+    mq_record r;
+    memset(&r, 0, sizeof r);
+    if (which == 1) {
+        rc = fetch_snapshot(h, s->best, chain, buf, &r);
+        if (rc != MQ_OK) return rc;
+        r.kind = MQ_REC_BEST;
+        r.code = 'F';
+    } else {
+        // current state: copy through the `best` path into a temporary snapshot is not needed -- read it directly
+        mq_models m;
+        memset(&m, 0, sizeof m);
+        const size_t md = h->md, ne = h->ne, ns = h->ns, n = h->n;
+        std::vector<int32_t> dim(n);
+        std::vector<float> z(n * md), vp(n * md), vpvs(n * md), eq(n * ne * 3), pres(n * ns), sres(n * ns), noise(n * 8), origin(n * ne);
+        m.n_chains = h->n; m.max_dim = h->md; m.n_events = h->ne; m.n_stations = h->ns;
+        m.dim = dim.data(); m.z = z.data(); m.vp = vp.data(); m.vpvs = vpvs.data(); m.eq = eq.data(); m.pres = pres.data();
+        m.sres = sres.data(); m.noise = noise.data(); m.origin = origin.data();
+        rc = mq_get_models(hh, &m);
+        if (rc != MQ_OK) return rc;
+        double rms = 0;
+        int64_t acce = 0;
+        MQ_CUDA(cudaMemcpy(&rms, h->rms + chain, sizeof rms, cudaMemcpyDeviceToHost));
+        MQ_CUDA(cudaMemcpy(&acce, s->acce + chain, sizeof acce, cudaMemcpyDeviceToHost));
+        r.chain = chain; r.kind = MQ_REC_CURRENT; r.code = 'S'; r.number = acce > 0 ? acce - 1 : 0; r.dim = dim[chain]; r.rms = rms;
+        r.z = z.data() + chain * md; r.vp = vp.data() + chain * md; r.vpvs = vpvs.data() + chain * md;
+        r.eq = eq.data() + chain * ne * 3; r.origin = origin.data() + chain * ne; r.pres = pres.data() + chain * ns;
+        r.sres = sres.data() + chain * ns; r.noise = noise.data() + 8 * (size_t)chain;
+        fn(user, &r);
+        return MQ_OK;
+    }
+    fn(user, &r);
+    return MQ_OK;
+}

@@ -29,17 +29,20 @@ eik_generic_kernel(EikBatch b)
     const int nodes = b.nxmod * b.nz;
     float* W = b.scratch + (size_t)warp * (((size_t)nodes + kFineNodes) * 32) + lane;
     float* WF = W + (size_t)nodes * 32;
-    const int n_tasks = (b.n_solves + 31) >> 5;
+    const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
+    const int n_solves = b.src_iz ? b.n_solves : n_items * b.nz;
+    const int n_tasks = (n_solves + 31) >> 5;
 
     for (int task = warp; task < n_tasks; task += n_warps) {
         const int g = task * 32 + lane;
-        if (g < b.n_solves) {
+        if (g < n_solves) {
             int iz, item;
             if (b.src_iz) { iz = b.src_iz[g]; item = g; }
-            else { iz = g / b.n_items; item = g - iz * b.n_items; }
+            else { iz = g / n_items; item = g - iz * n_items; }
             const float* s = b.slow + (size_t)item * b.nz;
             const int rc = eik::solve(s, 1, b.nxmod, b.nz, iz, W, WF, 32, nullptr);
             if (b.status) b.status[g] = rc;
+            if (b.status_min && rc < 0) atomicMin(b.status_min, rc);
             if (b.full_out) {
                 float* o = b.full_out + (size_t)g * nodes;
                 for (int i = 0; i < nodes; i++) o[i] = W[(size_t)i * 32];
@@ -59,8 +62,9 @@ eik_generic_kernel(EikBatch b)
 
 cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream)
 {
-    if (b.n_solves <= 0) return cudaSuccess;
-    const int n_tasks = (b.n_solves + 31) / 32;
+    const int n_solves = b.src_iz ? b.n_solves : b.n_items * b.nz;   // upper bound when n_items_dev is set
+    if (n_solves <= 0) return cudaSuccess;
+    const int n_tasks = (n_solves + 31) / 32;
     const int warps = n_tasks < b.max_warps ? n_tasks : b.max_warps;
     const int wpb = 4;
     const int blocks = (warps + wpb - 1) / wpb;

@@ -16,6 +16,8 @@ struct EikBatch {
     // "list mode" (src_iz != nullptr): solve g uses column g and source depth src_iz[g].
     const float* slow;        // [n_items][nz] device, h / v per depth cell
     int n_items;
+    const int32_t* n_items_dev; // table mode only: when non-null the item count is read on the device
+                                // (n_items is then the upper bound the grid is sized for)
     const int32_t* src_iz;    // [n_solves] device or nullptr
     int n_solves;
     // Outputs (device).  full_out: [n_solves][nxmod*nz] in the reference layout (x*nz+y).
@@ -28,6 +30,7 @@ struct EikBatch {
     const int32_t* rows;      // [n_rows] device: grid rows (receiver layers) that are kept
     int n_rows, xpitch;
     int32_t* status;          // [n_solves] device or nullptr
+    int32_t* status_min;      // [1] device or nullptr: atomicMin of every solve's status
     // Scratch: per resident warp (nxmod*nz + kFineNodes) * 32 floats.
     float* scratch;
     int max_warps;

@@ -1,0 +1,312 @@
+// forward.cu -- rasterise + travel-time lookup + residual/misfit kernels (sm_100a).
+//
+// Reference: setup_table_new's rasteriser (src/misfit.c:205-266), traveltimet
+// (src/interpol.c:43-83), dst (src/mcmc_eq.c:1303-1306) and the residual loop of
+// cal_fit_newx (src/misfit.c:83-153), for all chains at once.
+#include "forward.cuh"
+#include "eikonal.cuh"
+#include "launch_count.h"
+
+namespace mq {
+
+// ---- work list for "all chains" ---------------------------------------------------------
+__global__ void build_items_all_kernel(int n, int calct, size_t tab_stride, float* tab, const int32_t* tbuf,
+                                       int32_t* item_chain, int32_t* item_phase, float** item_tab, int32_t* n_items)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = (calct == 3) ? 2 : 1;
+    if (c == 0) *n_items = n * per;
+    if (c >= n) return;
+    int k = 0;
+    for (int ph = 0; ph < 2; ph++) {
+        if (!(calct & (1 << ph))) continue;
+        const int item = c * per + k++;
+        item_chain[item] = c;
+        item_phase[item] = ph;
+        item_tab[item] = tab + (((size_t)tbuf[2 * c + ph] * n + c) * 2 + ph) * tab_stride;
+    }
+}
+
+cudaError_t launch_build_items_all(Handle* h, const EvalView& v, int calct)
+{
+    build_items_all_kernel<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->n, calct, h->tab_stride, h->tab, v.tbuf,
+                                                                      h->item_chain, h->item_phase, h->item_tab, h->n_items);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- Voronoi rasteriser -------------------------------------------------------------------
+// One thread per (item, depth node).  Nearest nucleus in depth, ties -> highest index
+// (find_in_cell, src/mod_grd.c:93-110); vs = vp/vpvs; slow = h/v (src/misfit.c:209-213,263).
+__global__ void rasterise_kernel(int nz, int md, int n, float hgrid, float z0, const int32_t* n_items,
+                                 const int32_t* item_chain, const int32_t* item_phase, const int32_t* mbuf,
+                                 const int32_t* dim, const float* z, const float* vp, const float* vpvs, float* slow)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int item = t / nz, iz = t - item * nz;
+    if (item >= *n_items) return;
+    const int c = item_chain[item];
+    const int b = mbuf[c];
+    const size_t mo = ((size_t)b * n + c) * md;
+    const int d = dim[b * n + c];
+    const float zq = __fadd_rn(z0, __fmul_rn((float)iz, hgrid));
+    float best = 3.402823466e+38f;
+    int k = 0;
+    for (int i = 0; i < d; i++) {
+        const float dz = __fsub_rn(z[mo + i], zq);
+        const float d2 = __fmul_rn(dz, dz);
+        if (d2 <= best) { best = d2; k = i; }
+    }
+    const float p = vp[mo + k];
+    const float v = item_phase[item] == 0 ? p : __fdiv_rn(p, vpvs[mo + k]);
+    slow[(size_t)item * nz + iz] = __fdiv_rn(hgrid, v);
+}
+
+cudaError_t launch_rasterise(Handle* h, const EvalView& v, int max_items)
+{
+    const int threads = max_items * h->nz;
+    if (threads <= 0) return cudaSuccess;
+    rasterise_kernel<<<(threads + 127) / 128, 128, 0, h->stream>>>(h->nz, h->md, h->n, h->cfg.grid.h, h->cfg.grid.z0,
+                                                                    h->n_items, h->item_chain, h->item_phase, v.mbuf, h->dim,
+                                                                    h->z, h->vp, h->vpvs, h->slow);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tables(Handle* h, int max_items)
+{
+    EikBatch b = {};
+    b.nxmod = h->nxmod; b.nz = h->nz;
+    b.slow = h->slow; b.n_items = max_items; b.n_items_dev = h->n_items;
+    b.row_out = h->item_tab; b.rows = h->d_rows; b.n_rows = h->n_rows; b.xpitch = h->xp;
+    b.status_min = h->solve_status;
+    b.scratch = h->scratch; b.max_warps = h->scratch_warps;
+    return eik_launch_generic(b, h->stream);
+}
+
+// ---- travel-time lookup -------------------------------------------------------------------
+// Bilinear interpolation weights of (dist, z) in a [nz][xp] receiver-row table; the same
+// arithmetic as traveltimet (src/interpol.c:56-80): float corner products summed left to right,
+// the 1/(dx*dy) prefactor in double.
+struct Bilinear {
+    int m1, iz1;
+    float a, b, c, d;   // x2-x, x-x1, y2-y, y-y1
+    double pref;
+    bool oob;
+};
+
+__device__ __forceinline__ Bilinear bilinear_setup(float dist, float z, float hgrid, float z0, int nxmod, int nz)
+{
+    Bilinear w;
+    w.m1 = (int)__fdiv_rn(dist, hgrid);
+    const float y = __fsub_rn(z, z0);
+    w.iz1 = (int)__fdiv_rn(y, hgrid);
+    w.oob = (w.m1 >= nxmod - 1 || w.iz1 >= nz - 1);
+    const float x1 = __fmul_rn((float)w.m1, hgrid), x2 = __fmul_rn((float)(w.m1 + 1), hgrid);
+    const float y1 = __fmul_rn((float)w.iz1, hgrid), y2 = __fmul_rn((float)(w.iz1 + 1), hgrid);
+    w.a = __fsub_rn(x2, dist); w.b = __fsub_rn(dist, x1);
+    w.c = __fsub_rn(y2, y);    w.d = __fsub_rn(y, y1);
+    w.pref = 1.0 / (double)__fsub_rn(x2, x1) / (double)__fsub_rn(y2, y1);
+    return w;
+}
+
+__device__ __forceinline__ float bilinear_eval(const Bilinear& w, const float* __restrict__ row, int xp)
+{
+    if (w.oob) return 1e30f;
+    const float* p = row + (size_t)w.iz1 * xp + w.m1;
+    const float v1 = __ldg(p), v2 = __ldg(p + 1), v3 = __ldg(p + xp), v4 = __ldg(p + xp + 1);
+    float s = __fmul_rn(__fmul_rn(v1, w.a), w.c);
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v2, w.b), w.c));
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v3, w.a), w.d));
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v4, w.b), w.d));
+    return (float)(w.pref * (double)s);
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- residuals / origin time / class sums --------------------------------------------------
+// One warp per (chain, event): lanes stride over the event's picks (P first, then S).
+struct MisfitParams {
+    int n, ne, ns, np, nz, nxmod, xp, md;
+    float hgrid, z0;
+    int eikonal, scor_flag;
+    size_t tab_stride;
+    DevPicks pk;
+    EvalView v;
+    const int32_t* dim;
+    const float *z, *vp, *vpvs;
+    const float *eq, *pres, *sres;
+    const float* tab;
+    float *evsum, *origin, *evq, *oq;
+    float *resid, *tpred;
+    int32_t* err;
+};
+
+__global__ void __launch_bounds__(128) misfit_kernel(MisfitParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const long task = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (task >= (long)p.n * p.ne) return;
+    const int c = (int)(task / p.ne), e = (int)(task - (long)c * p.ne);
+    const int only = p.v.ev_only[c];
+    if (only == -2 || (only >= 0 && only != e)) return;
+
+    float ex, ey, ez;
+    if (p.v.q_idx[c] == e) { ex = p.v.q_xyz[3 * c]; ey = p.v.q_xyz[3 * c + 1]; ez = p.v.q_xyz[3 * c + 2]; }
+    else { const float* q = p.eq + ((size_t)c * p.ne + e) * 3; ex = q[0]; ey = q[1]; ez = q[2]; }
+
+    const int ridx = p.v.r_idx[c];
+    const float* rd = p.v.r_d + 4 * (size_t)c;
+    const float nsm1 = (float)(p.ns - 1);
+    const float* pres = p.pres + (size_t)c * p.ns;
+    const float* sres = p.sres + (size_t)c * p.ns;
+
+    const int b = p.pk.ev_off[e], end = p.pk.ev_off[e + 1], npk = p.pk.n_p[e];
+    const float* tabP = p.tab + (((size_t)p.v.tbuf[2 * c] * p.n + c) * 2 + 0) * p.tab_stride;
+    const float* tabS = p.tab + (((size_t)p.v.tbuf[2 * c + 1] * p.n + c) * 2 + 1) * p.tab_stride;
+    const size_t rowsz = (size_t)p.nz * p.xp;
+    float* resid = p.resid + (size_t)c * p.np;
+
+    // straight-ray branch (eikonal == 0, src/misfit.c:90,108): velocity of the nucleus nearest to z = 0
+    float v0p = 1.f, v0s = 1.f;
+    if (p.eikonal == 0) {
+        const int mb = p.v.mbuf[c];
+        const size_t mo = ((size_t)mb * p.n + c) * p.md;
+        const int d = p.dim[mb * p.n + c];
+        float best = 3.402823466e+38f;
+        int k = 0;
+        for (int i = 0; i < d; i++) {
+            const float d2 = __fmul_rn(p.z[mo + i], p.z[mo + i]);
+            if (d2 <= best) { best = d2; k = i; }
+        }
+        v0p = p.vp[mo + k];
+        v0s = __fdiv_rn(v0p, p.vpvs[mo + k]);
+    }
+
+    float sum = 0.f;
+    bool oob = false;         // a pick fell outside the table (1e30 sentinel of src/interpol.c:64-65)
+    unsigned present = 0u;    // classes that occur in this event
+    for (int j = b + lane; j < end; j += 32) {
+        const bool isS = (j - b) >= npk;
+        const float dx = __fsub_rn(p.pk.x[j], ex), dy = __fsub_rn(p.pk.y[j], ey);
+        const float dist = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        float tt;
+        if (p.eikonal == 0) {
+            const float r2 = __fadd_rn(__fmul_rn(dist, dist), __fmul_rn(ez, ez));
+            tt = (float)(sqrt((double)r2) / (double)(isS ? v0s : v0p));
+        } else {
+            const Bilinear w = bilinear_setup(dist, ez, p.hgrid, p.z0, p.nxmod, p.nz);
+            oob = oob || w.oob;
+            const float* row = (isS ? tabS : tabP) + (size_t)p.pk.r0[j] * rowsz;
+            const float t1 = bilinear_eval(w, row, p.xp);
+            const float t2 = bilinear_eval(w, row + rowsz, p.xp);
+            tt = __fadd_rn(__fmul_rn(t1, p.pk.w1[j]), __fmul_rn(t2, p.pk.w2[j]));
+        }
+        const int st = p.pk.st_id[j];
+        float corr = isS ? sres[st] : pres[st];
+        if (ridx >= 0) {   // proposed station-correction perturbation (src/mcmc_eq.c:910-928)
+            const float d1 = isS ? rd[1] : rd[0], d2 = isS ? rd[3] : rd[2];
+            if (p.scor_flag <= 0) corr = (st == ridx) ? __fadd_rn(corr, d1) : __fsub_rn(corr, __fdiv_rn(d1, nsm1));
+            if (p.scor_flag != 0 && st == ridx) corr = __fadd_rn(corr, d2);
+        }
+        if (corr < -1000.f) atomicExch(p.err, MQ_ERR_STATCOR);
+        tt = __fadd_rn(tt, corr);
+        const float diff = __fsub_rn(tt, p.pk.t[j]);
+        resid[j] = diff;
+        if (p.tpred) p.tpred[(size_t)c * p.np + j] = tt;
+        sum += diff;
+    }
+    sum = warp_sum(sum);
+    const float mean = sum / (float)(end - b);
+    __syncwarp();
+
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = b + lane; j < end; j += 32) {
+        const float d = __fsub_rn(resid[j], mean);
+        if (p.tpred) resid[j] = d;
+        const float d2 = d * d;
+        const int cp = p.pk.cp[j];
+        present |= 1u << cp;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += (cp == k) ? d2 : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = warp_sum(acc[k]);
+    // With a 1e30 prediction in the event every de-meaned residual of it is ~1e29 or more and its
+    // square overflows FP32 in the reference: the event's classes get an infinite misfit.  Stated
+    // explicitly here because the overflow would otherwise depend on the summation order.
+    if (__any_sync(0xffffffffu, oob)) {
+        present = __reduce_or_sync(0xffffffffu, present);
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (present & (1u << k)) acc[k] = __int_as_float(0x7f800000);
+    }
+    if (lane == 0) {
+        if (only >= 0) {
+            for (int k = 0; k < 8; k++) p.evq[8 * (size_t)c + k] = acc[k];
+            p.oq[c] = -mean;
+        } else {
+            const int eb = p.v.ebuf[c];
+            float* o = p.evsum + (((size_t)eb * p.n + c) * p.ne + e) * 8;
+            for (int k = 0; k < 8; k++) o[k] = acc[k];
+            p.origin[((size_t)eb * p.n + c) * p.ne + e] = -mean;
+        }
+    }
+}
+
+cudaError_t launch_misfit(Handle* h, const EvalView& v)
+{
+    MisfitParams p;
+    p.n = h->n; p.ne = h->ne; p.ns = h->ns; p.np = h->np; p.nz = h->nz; p.nxmod = h->nxmod; p.xp = h->xp; p.md = h->md;
+    p.hgrid = h->cfg.grid.h; p.z0 = h->cfg.grid.z0; p.eikonal = h->cfg.eikonal; p.scor_flag = h->cfg.scor_flag;
+    p.tab_stride = h->tab_stride; p.pk = h->pk; p.v = v; p.dim = h->dim; p.z = h->z; p.vp = h->vp; p.vpvs = h->vpvs;
+    p.eq = h->eq; p.pres = h->pres; p.sres = h->sres; p.tab = h->tab; p.evsum = h->evsum; p.origin = h->origin;
+    p.evq = h->evq; p.oq = h->oq; p.resid = h->resid; p.tpred = h->want_pred ? h->tpred : nullptr; p.err = h->err;
+    const long tasks = (long)h->n * h->ne;
+    const int wpb = 4;
+    misfit_kernel<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- per-chain totals -----------------------------------------------------------------------
+// One warp per chain; double accumulation over events in a fixed order (deterministic).
+__global__ void __launch_bounds__(128) totals_kernel(int n, int ne, EvalView v, const int32_t* ecur, const float* evsum,
+                                                     const float* evq, const float* mf_cur, float* mf_eval)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const int only = v.ev_only[c];
+    if (only == -2) {   // nothing re-evaluated (noise proposal): the sums are those of the current model
+        if (lane < 8) mf_eval[8 * (size_t)c + lane] = mf_cur[8 * (size_t)c + lane];
+        return;
+    }
+    const int eb = (only >= 0) ? ecur[c] : v.ebuf[c];
+    const float* src = evsum + ((size_t)eb * n + c) * ne * 8;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int e = lane; e < ne; e += 32) {
+        const float* s = (e == only) ? evq + 8 * (size_t)c : src + (size_t)e * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += (double)s[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane == 0)
+        for (int k = 0; k < 8; k++) mf_eval[8 * (size_t)c + k] = (float)acc[k];
+}
+
+cudaError_t launch_totals(Handle* h, const EvalView& v)
+{
+    const int wpb = 4;
+    totals_kernel<<<(h->n + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(h->n, h->ne, v, h->ecur, h->evsum, h->evq, h->mf,
+                                                                       h->mf_eval);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace mq

@@ -1,0 +1,18 @@
+// forward.cuh -- launchers of the forward-model kernels (rasterise, misfit, totals).
+#pragma once
+#include "state.h"
+
+namespace mq {
+
+// items for "rebuild the tables of every chain" (mq_forward): phases selected by calct (1 P, 2 S, 3 both)
+cudaError_t launch_build_items_all(Handle* h, const EvalView& v, int calct);
+// slow[item][iz] = h / v(z0 + iz*h) from the model the view points at (src/misfit.c:205-214,256-266)
+cudaError_t launch_rasterise(Handle* h, const EvalView& v, int max_items);
+// eikonal for every item x source depth into the item's table (src/misfit.c:270-289)
+cudaError_t launch_tables(Handle* h, int max_items);
+// residuals, origin times and per-event class sums (src/misfit.c:83-153)
+cudaError_t launch_misfit(Handle* h, const EvalView& v);
+// per-chain class sums mf_eval[c][8] from the per-event sums of the view
+cudaError_t launch_totals(Handle* h, const EvalView& v);
+
+}  // namespace mq

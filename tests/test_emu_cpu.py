@@ -1,0 +1,70 @@
+"""The CUDA solver core (csrc/eik_core.cuh) compiled for the HOST: the same FP32, restructured
+algorithm the GPU runs, checked against the oracle on CPU.  Tolerance: |dT| <= max(1e-4 s, 2e-6 T)
+(SURVEY.md Appendix A.5).  This is a test of the algorithm, not a product path."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import util
+from tests.util import ptr, fp
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from mcmc_eq_b200 import build
+    L = C.CDLL(build.build_emu())
+    L.emu_time_2d.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, C.POINTER(C.c_int)]
+    return L
+
+
+def _run(emu, s, nx, iz):
+    s = util.f32(s)
+    t = np.zeros((nx, len(s)), np.float32)
+    cnt = np.zeros(7, np.int32)
+    rc = emu.emu_time_2d(ptr(s), nx, len(s), iz, ptr(t), cnt.ctypes.data_as(C.POINTER(C.c_int)))
+    return t, rc, cnt
+
+
+def test_core_matches_golden(emu):
+    d = np.load(os.path.join(util.GOLDEN, "eikonal_ref.npz"))
+    worst = 0.0
+    tot = np.zeros(7, np.int64)
+    for i, m in enumerate(d["meta"]):
+        s, tref = d[f"s_{i}"], d[f"t_{i}"]
+        t, rc, cnt = _run(emu, s, tref.shape[0], int(m.split("|")[2]))
+        assert rc == 0
+        err = np.abs(t - tref)
+        assert (err <= util.eikonal_tol(tref)).all(), (m, err.max())
+        worst = max(worst, float(err.max()))
+        tot += cnt
+    assert worst < 1e-4
+    assert tot[2] > 0 and tot[3] > 0 and tot[4] > 0 and tot[5] > 0 and tot[6] > 0   # every branch taken
+
+
+@pytest.mark.parametrize("grid,kind", [(util.EXAMPLE2_GRID, "posterior"), (util.EXAMPLE_GRID, "posterior"),
+                                       (util.EXAMPLE_GRID, "contrast"), (util.EXAMPLE2_GRID, "lvz")])
+def test_core_matches_oracle_all_depths(emu, oracle, grid, kind):
+    rng = np.random.default_rng(abs(hash((grid["nz"], kind))) % 2**32)
+    nx, nz = util.nxmod_of(grid), grid["nz"]
+    z, vp, vpvs = util.voronoi_model(rng, int(rng.integers(2, 21)), grid["z0"], grid["z0"] + (nz - 1) * grid["h"], kind)
+    for ps in (1, 2):
+        s = util.rasterise_np(z, vp, vpvs, grid["h"], grid["z0"], nz, ps)
+        for iz in range(nz):
+            tref, _ = util.oracle_time_2d(s, nx, iz)
+            t, rc, _ = _run(emu, s, nx, iz)
+            assert rc == 0
+            assert (np.abs(t - tref) <= util.eikonal_tol(tref)).all()
+
+
+def test_core_small_and_degenerate_grids(emu, oracle):
+    rng = np.random.default_rng(3)
+    for nx, nz in ((2, 2), (2, 9), (9, 2), (3, 3), (11, 5), (12, 23), (40, 8)):
+        z, vp, vpvs = util.voronoi_model(rng, 3, 0.0, float(nz - 1), "contrast")
+        s = util.rasterise_np(z, vp, vpvs, 1.0, 0.0, nz, 1)
+        for iz in range(nz):
+            tref, r1 = util.oracle_time_2d(s, nx, iz)
+            t, r2, _ = _run(emu, s, nx, iz)
+            assert r1 == 0 and r2 == 0
+            assert (np.abs(t - tref) <= util.eikonal_tol(tref)).all(), (nx, nz, iz)

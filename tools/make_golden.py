@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* from the UNMODIFIED reference (run in the build container only).
+
+  inputs_example{,2}.json/.npz : the two shipped data sets, parsed (configs 1 and 2 of BASELINE.json)
+  eikonal_ref.npz              : time_2d fields of the compiled reference (oracle/_ref) for seeded models
+  forward_ref.npz              : cal_fit_newx class sums / origin times of the compiled reference
+  chain_ref_example2.out       : a short fixed-seed chain of the reference mcmc_eq binary
+
+Usage: python tools/make_golden.py   (needs /root/reference and oracle/_ref built: make -C oracle)
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import util, inputs, refapi  # noqa: E402
+import mcmc_eq_b200 as mq  # noqa: E402  (only its file readers are used here, no GPU)
+
+REF = "/root/reference"
+G = util.GOLDEN
+
+
+def cfg_to_dict(c):
+    d = {}
+    for name, _t in c._fields_:
+        v = getattr(c, name)
+        if name == "grid":
+            for gname, _ in v._fields_:
+                d[gname] = getattr(v, gname)
+        elif isinstance(v, bytes):
+            d[name] = v.decode()
+        else:
+            d[name] = v
+    # keep the short decimal text of float fields (2.0 not 2.000000047)
+    return {k: (float(np.format_float_positional(np.float32(v), unique=True)) if isinstance(v, float) else v) for k, v in d.items()}
+
+
+def parse_t64(path):
+    t = []
+    for line in open(path):
+        if "#" in line or not line.strip():
+            continue
+        t.append(float(line.split()[6]))
+    return np.array(t)
+
+
+def inputs_of(name, cfg_path, picks_path):
+    c = mq.read_config(cfg_path)
+    pk = mq.Picks.read(picks_path)
+    # t as printed in the file (double), in file order -> our order (P first then S per event)
+    t_file = parse_t64(picks_path)
+    # recover the permutation: within each event P picks (file order) then S picks (file order)
+    phases = [line.split()[2] for line in open(picks_path) if "#" not in line and line.strip()]
+    order = []
+    k = 0
+    for e in range(pk.n_events):
+        n = pk.ev_off[e + 1] - pk.ev_off[e]
+        idx = list(range(k, k + n))
+        order += [i for i in idx if "P" in phases[i]] + [i for i in idx if "P" not in phases[i]]
+        k += n
+    t64 = t_file[order]
+    assert np.array_equal(t64.astype(np.float32), pk.t)
+    with open(os.path.join(G, f"inputs_{name}.json"), "w") as f:
+        json.dump(cfg_to_dict(c), f, indent=1)
+    np.savez_compressed(os.path.join(G, f"inputs_{name}.npz"), ev_off=pk.ev_off, n_p=pk.n_p, st_id=pk.st_id.astype(np.int16),
+                        x=pk.x, y=pk.y, z=pk.z, t64=t64, cls=pk.cls.astype(np.int8), reftime=pk.reftime, fix=pk.fix)
+
+
+def eikonal_fields():
+    rng = np.random.default_rng(20241018)
+    out = {}
+    cases = []
+    for gname, g in (("ex2", util.EXAMPLE2_GRID), ("ex", util.EXAMPLE_GRID)):
+        nx, nz = util.nxmod_of(g), g["nz"]
+        for kind in ("posterior", "contrast", "lvz"):
+            z, vp, vpvs = util.voronoi_model(rng, int(rng.integers(2, 18)), g["z0"], g["z0"] + (nz - 1) * g["h"], kind)
+            s = util.rasterise_np(z, vp, vpvs, g["h"], g["z0"], nz, 1)
+            for iz in (0, 9, 10, 11, nz // 2, nz - 2, nz - 1)[:: (1 if gname == "ex2" else 3)]:
+                t, rc = util.ref_time_2d(s, nx, iz)
+                assert rc == 0
+                cases.append((gname, kind, iz))
+                out[f"s_{len(cases) - 1}"] = s
+                out[f"t_{len(cases) - 1}"] = t
+    # tiny grids: every source depth
+    for nx, nz, nl in ((12, 8, 2), (30, 25, 4), (9, 40, 6)):
+        z, vp, vpvs = util.voronoi_model(rng, nl, 0.0, (nz - 1) * 1.0, "contrast")
+        s = util.rasterise_np(z, vp, vpvs, 1.0, 0.0, nz, 1)
+        for iz in range(nz):
+            t, rc = util.ref_time_2d(s, nx, iz)
+            cases.append((f"tiny{nx}x{nz}", "contrast", iz))
+            out[f"s_{len(cases) - 1}"] = s
+            out[f"t_{len(cases) - 1}"] = t
+    out["meta"] = np.array([f"{a}|{b}|{c}" for a, b, c in cases])
+    np.savez_compressed(os.path.join(G, "eikonal_ref.npz"), **out)
+    print("eikonal_ref:", len(cases), "fields")
+
+
+def forward_ref():
+    """cal_fit_newx of the compiled reference on seeded chain states of both examples."""
+    from tests import fwd_helpers as fh
+    ref = util.reflib()
+    out = {}
+    for name, sub, pickfile, nstates in (("example2", "Example2", "picks.mcmc", 3), ("example", "Example", "picks_synth", 2)):
+        cfgp, pkp = os.path.join(REF, sub, "config_eqx.dat"), os.path.join(REF, sub, pickfile)
+        c = mq.read_config(cfgp)
+        pk = mq.Picks.read(pkp)
+        g = dict(h=c.grid.h, nx=c.grid.nx, ny=c.grid.ny, nz=c.grid.nz, x0=c.grid.x0, y0=c.grid.y0, z0=c.grid.z0)
+        rf = refapi.RefForward(ref, g, pkp)
+        assert rf.ne == pk.n_events and rf.nos == pk.n_stations
+        rng = np.random.default_rng(7 if name == "example" else 8)
+        states = fh.random_states(rng, c, pk, nstates, "posterior")
+        for i, s in enumerate(states):
+            mf, org = rf.forward(s["z"], s["vp"], s["vpvs"], s["eq"], s["pres"], s["sres"], 3, 1)
+            for k, v in s.items():
+                out[f"{name}_{i}_{k}"] = v
+            out[f"{name}_{i}_mf"] = mf
+            out[f"{name}_{i}_origin"] = org
+            if i == 0:   # a few table rows of the reference: receiver rows 1,2 of the P table, every source depth
+                tp = rf.table(1)
+                out[f"{name}_{i}_tabP_rows12"] = tp[1:3]
+        out[f"{name}_n"] = np.array(nstates)
+    np.savez_compressed(os.path.join(G, "forward_ref.npz"), **out)
+    print("forward_ref done")
+
+
+def chain_ref():
+    """Short fixed-seed chain of the reference binary on Example2 (byte-reproducible)."""
+    exe = os.path.join(util.REF_DIR, "mcmc_eq")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=77)
+        outp = os.path.join(d, "rjx-000.out")
+        subprocess.run([exe, cfgp, outp, pkp], check=True, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        txt = open(outp).read()
+    open(os.path.join(G, "chain_ref_example2.out"), "w").write(txt)
+    print("chain_ref:", txt.count("\n"), "lines")
+
+
+if __name__ == "__main__":
+    os.makedirs(G, exist_ok=True)
+    inputs_of("example", os.path.join(REF, "Example/config_eqx.dat"), os.path.join(REF, "Example/picks_synth"))
+    inputs_of("example2", os.path.join(REF, "Example2/config_eqx.dat"), os.path.join(REF, "Example2/picks.mcmc"))
+    eikonal_fields()
+    forward_ref()
+    chain_ref()
+    print(subprocess.run(["du", "-sh", G], capture_output=True, text=True).stdout)
