@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- MCMC proposals/s including the full FD travel-time forward, on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps K --warmup W      # the reference's own CPU path
+
+Workload (BASELINE.json configs[2]): 1024 chains per GPU x 200 events x 50
+stations (20 000 picks), Example grid (282 x 62 eikonal plane), models of up to 20 layers.  A step is one
+Metropolis-Hastings iteration of every chain with a velocity-model proposal ('P': both travel-time tables are
+rebuilt = 2*nz eikonal solves, then the full misfit) -- "P_full" of SURVEY.md section 8d.  Chains are
+independent, so N GPUs run N*1024 chains with no data-path collective (weak scaling).
+
+value = whole-job proposals/s with the chain state resident in HBM (device-timed, max over ranks);
+e2e   = forward evaluations/s through the batched drop-in of cal_fit_newx (mq_forward_host): models are
+        copied from pinned host memory every call and the class sums + origin times are read back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mcmc_proposals_per_sec_incl_fd_traveltime_forward"
+UNIT = "proposals/s"
+SMEM_PEAK_GBS = 148 * 128 * 1.965   # 148 SM x 128 B/clk x 1.965 GHz = 37.2 TB/s
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not rows:
+            return None
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def barrier_max(dist, value, device):
+    """barrier + max over ranks of a python float"""
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{device}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------------
+# the reference's own CPU path: oracle/_ref/mcmc_eq (unmodified sources, gcc -O4), one process per host core
+# ------------------------------------------------------------------------------------------------------
+def reference_exe():
+    p = os.path.join(ROOT, "oracle", "_ref", "mcmc_eq")
+    return p if os.path.exists(p) else None
+
+
+def run_reference_batch(workdir, exe, cfg_dict, cores, accepted, seed0):
+    """`cores` concurrent chains of `accepted` accepted models each, proposal string 'P' (every proposal rebuilds
+    both tables).  Returns (proposals, wall seconds)."""
+    from mcmc_eq_b200.io import write_config
+    procs = []
+    t0 = time.perf_counter()
+    for k in range(cores):
+        cfgp = os.path.join(workdir, f"cfg_{k}.dat")
+        a = max(1, accepted // 3)
+        write_config(cfg_dict, cfgp, j_max_start=a, j_max_main=max(1, accepted - a), deci=10**8, true_random=seed0 + k,
+                     dstring_start="P", dstring_main="P")
+        cmd = [exe, cfgp, os.path.join(workdir, f"rjx-{k:03d}.out"), os.path.join(workdir, "picks")]
+        if shutil.which("taskset"):
+            cmd = ["taskset", "-c", str(k)] + cmd
+        procs.append(subprocess.Popen(cmd, cwd=workdir, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    for p in procs:
+        p.wait()
+    wall = time.perf_counter() - t0
+    proposals = 0
+    for k in range(cores):
+        txt = open(os.path.join(workdir, f"rjx-{k:03d}.out")).read()
+        m = re.search(r"cnt RMS tested\s+(\d+)", txt)
+        proposals += int(m.group(1)) if m else 0
+    return proposals, wall
+
+
+def oracle_port_batch(cfg, pk, truth, seconds):
+    """Fallback when the compiled reference is absent: time the oracle port (1 core) of a full forward."""
+    from tests import fwd_helpers as fh
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        fh.oracle_forward(cfg, pk, truth["z"], truth["vp"], truth["vpvs"], truth["eq"], truth["pres"], truth["sres"])
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, pk, truth, budget_s, steps=1, warmup=0):
+    """Reference CPU path on this box's host cores, bounded sample.  -> dict for the JSON line + per-step list."""
+    from mcmc_eq_b200.io import config_to_dict, write_picks
+    exe = reference_exe()
+    cores = os.cpu_count() or 1
+    if exe is None:
+        n, wall = oracle_port_batch(cfg, pk, truth, min(budget_s, 20.0))
+        return {"value": n / wall, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{n} full forwards (2*nz eikonal solves + misfit) of the oracle port, one chain, {wall:.1f} s"}, wall
+    d = tempfile.mkdtemp(prefix="mqref_")
+    try:
+        write_picks(pk, os.path.join(d, "picks"), truth["t64"])
+        cd = config_to_dict(cfg)
+        # calibrate: a very short batch tells how many proposals one accepted model costs and how fast they are
+        p0, w0 = run_reference_batch(d, exe, cd, cores, 3, 1000)
+        rate = max(p0 / max(w0, 1e-3), 1e-3)                       # proposals/s, all cores
+        per_acc = max(p0 / (3.0 * cores), 1.0)
+        per_step = budget_s / max(steps + warmup, 1)
+        accepted = int(max(3, min(400, (rate / cores) * per_step * 0.8 / per_acc)))
+        tot_p, tot_w = 0, 0.0
+        for s in range(warmup + steps):
+            p, w = run_reference_batch(d, exe, cd, cores, accepted, 2000 + 100 * s)
+            if s >= warmup:
+                tot_p += p
+                tot_w += w
+        return {"value": tot_p / tot_w, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{steps} batch(es) of {cores} concurrent unmodified mcmc_eq processes (gcc -O4, one per core), "
+                          f"{accepted} accepted models each, proposal string 'P' on the same synthetic picks: "
+                          f"{tot_p} proposals in {tot_w:.1f} s"}, tot_w
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=1024, help="chains per GPU")
+    ap.add_argument("--events", type=int, default=200)
+    ap.add_argument("--stations", type=int, default=50)
+    ap.add_argument("--proposals", default="P", help="proposal letters of a step (P = full forward recomputation)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of host time for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    n_gpus = max(world, 1)
+    workload = (f"synth-{args.chains}: {args.chains} chains/GPU x {args.events} events x {args.stations} stations "
+                f"({2 * args.events * args.stations} picks), Example grid h=2 km 200x200x62 (eikonal plane 282x62), "
+                f"<=20 layers, proposal '{args.proposals}' (P_full: 2*nz eikonal solves + full misfit per proposal)")
+    config = {"workload": workload, "chains_per_gpu": args.chains, "events": args.events, "stations": args.stations,
+              "grid": "282x62", "proposal_string": args.proposals, "parallelism": f"chains sharded x{n_gpus}, no collective",
+              "l2": "per-step working set (tables 0.9 GB + solver scratch > 1 GB per GPU) exceeds the 126 MB L2"}
+
+    import mcmc_eq_b200 as mq
+    from mcmc_eq_b200 import synth
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cfg, pk, truth = synth.workload(args.events, args.stations, 33, 0)
+        base, wall = cpu_baseline(cfg, pk, truth, 150.0, steps=max(args.steps, 1), warmup=args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": base, "gpu_launches": 0,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    device = local
+    cfg, pk, truth = synth.workload(args.events, args.stations, 33, device, j_max_start=0, j_max_main=2**30, deci=2**30)
+    smp = mq.Sampler(cfg, pk, args.chains, device, 1000 + rank)
+    smp.init_chains()
+    # leave the start phase of the chain the way a real run does: a few hundred mixed iterations are not needed for
+    # timing (the cost of a 'P' step does not depend on the state), but the models must be valid chain states
+    for _ in range(W):
+        smp.step(1, args.proposals)
+    smp.sync()
+
+    # ---- timed region: K steps, device-timed on the library's stream --------------------------------------
+    clocks = ClockSampler(device)
+    clocks.start()
+    smp.profile(True)
+    launches0 = mq.lib().mq_launch_count()
+    barrier_max(dist, 0.0, device)
+    smp.sync()
+    smp.timer_start(0)
+    for _ in range(args.steps):
+        smp.step(1, args.proposals)
+    ms = smp.timer_stop(0)
+    smp.sync()
+    ms = barrier_max(dist, ms, device)
+    launches = mq.lib().mq_launch_count() - launches0
+    eik_ms, eik_n, solves_per_launch = smp.profile(False)
+    clk = clocks.stop()
+    counts, ll, rms = smp.stats()
+    proposals = args.chains * n_gpus * args.steps
+    value = proposals / (ms / 1000.0)
+
+    # ---- roofline of the dominant kernel (eikonal) ----------------------------------------------------------
+    nz, nxmod = cfg.grid.nz, smp.nxmod
+    alg_bytes_per_solve = 4 * nz + 4 * nxmod * nz            # read nz slownesses, write the field
+    peak, peak_src = measured_peak()
+    roofline = None
+    if eik_n > 0:
+        t_launch = eik_ms / eik_n / 1000.0
+        achieved = alg_bytes_per_solve * solves_per_launch / t_launch / 1e9
+        smem_alg = 32.0 * nxmod * nz * solves_per_launch / t_launch / 1e9
+        roofline = {"bound": "hbm", "kernel": "eik_generic_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_solve": alg_bytes_per_solve, "solves_per_launch": int(solves_per_launch),
+                    "avg_launch_ms": eik_ms / eik_n, "share_of_step": eik_ms / ms,
+                    "layout": "receiver rows only are stored (3 of 62 rows); algorithmic bytes count the full field as the reference materialises it",
+                    "smem": {"achieved": smem_alg, "peak": SMEM_PEAK_GBS, "unit": "GB/s", "frac": smem_alg / SMEM_PEAK_GBS,
+                             "algorithmic_bytes_per_node_update": 32}}
+
+    # ---- end to end through the plugin call with host buffers ----------------------------------------------
+    import torch
+    m = smp.get_models()
+    pinned = {}
+    for name in ("dim", "z", "vp", "vpvs", "eq", "pres", "sres", "noise", "origin"):
+        a = getattr(m, name)
+        t = torch.from_numpy(a.copy()).pin_memory()
+        pinned[name] = t
+        setattr(m, name, t.numpy())
+    mf_t = torch.zeros((args.chains, 8), dtype=torch.float32).pin_memory()
+    org_t = torch.zeros((args.chains, pk.n_events), dtype=torch.float32).pin_memory()
+    h2d = sum(getattr(m, k).nbytes for k in ("dim", "z", "vp", "vpvs", "eq", "pres", "sres", "noise"))
+    d2h = mf_t.numpy().nbytes + org_t.numpy().nbytes
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        smp.forward_host(m, 3, mf_t.numpy(), org_t.numpy())
+    barrier_max(dist, 0.0, device)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        smp.forward_host(m, 3, mf_t.numpy(), org_t.numpy())      # synchronous: returns with the results on the host
+    e2e_s = barrier_max(dist, time.perf_counter() - t0, device)
+    e2e = {"value": args.chains * n_gpus * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "call": "mq_forward_host(calct=3): batched drop-in of cal_fit_newx"}
+
+    base = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        base, _ = cpu_baseline(cfg, pk, truth, args.cpu_budget)
+    smp.close()
+    if rank != 0:
+        return
+    acc = float(counts[:, 17].sum()) / max(float(counts[:, 17].sum() + counts[:, 18].sum()), 1.0)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": base, "acceptance_rate": acc,
+            "median_rms_s": float(np.median(rms))}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -195,6 +195,17 @@ int mq_snapshot(mq_handle* h, int chain, int which, mq_record_fn fn, void* user)
 
 int mq_sync(mq_handle* h);
 
+/* Measurement aid for bench.py: with enable != 0 every eikonal launch is bracketed by CUDA events on
+ * the handle's stream.  Returns the time and number of launches accumulated since the previous call
+ * (and restarts the accumulation); solves_per_full_launch = 2 * n_chains * nz, the number of solves one
+ * launch performs when every chain rebuilds both tables. */
+int mq_profile(mq_handle* h, int enable, double* eikonal_ms, int64_t* eikonal_launches,
+               int64_t* solves_per_full_launch);
+
+/* CUDA-event stopwatch on the handle's stream: stop = 0 records the start of `slot` (0..15), stop = 1 records
+ * the end, waits for it and returns the device time between the two in *elapsed_ms. */
+int mq_timer(mq_handle* h, int slot, int stop, double* elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.mq_drain.argtypes = [C.c_void_p, RECORD_FN, C.c_void_p, C.POINTER(C.c_int)]
         L.mq_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_int, RECORD_FN, C.c_void_p]
         L.mq_sync.argtypes = [C.c_void_p]
+        L.mq_timer.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        L.mq_profile.argtypes = [C.c_void_p, C.c_int, dp, lp, lp]
         L.mqio_read_config.argtypes = [C.c_char_p, C.POINTER(MqConfig)]
         L.mqio_read_picks.argtypes = [C.c_char_p, C.POINTER(MqioPicks)]
         L.mqio_free_picks.argtypes = [C.POINTER(MqioPicks)]
@@ -275,6 +277,19 @@ class Sampler:
 
     def sync(self):
         check(lib().mq_sync(self.h))
+
+    def timer_start(self, slot=0):
+        check(lib().mq_timer(self.h, slot, 0, None))
+
+    def timer_stop(self, slot=0) -> float:
+        ms = C.c_double(0)
+        check(lib().mq_timer(self.h, slot, 1, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        ms, n, per = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        check(lib().mq_profile(self.h, int(enable), C.byref(ms), C.byref(n), C.byref(per)))
+        return ms.value, n.value, per.value
 
     def stats(self):
         counts = np.zeros((self.n, 20), np.int64)

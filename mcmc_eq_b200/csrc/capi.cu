@@ -105,6 +105,7 @@ extern "C" int mq_destroy(mq_handle* hh)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     sampler_destroy(h);
+    profile_destroy(h);
     cudaFree(h->pk.ev_off); cudaFree(h->pk.n_p); cudaFree(h->pk.st_id); cudaFree(h->pk.r0); cudaFree(h->pk.cp);
     cudaFree(h->pk.x); cudaFree(h->pk.y); cudaFree(h->pk.t); cudaFree(h->pk.w1); cudaFree(h->pk.w2); cudaFree(h->pk.fix);
     cudaFree(h->d_rows);
@@ -460,4 +461,39 @@ extern "C" int mq_get_predictions(mq_handle* hh, int chain, float* resid, float*
     if (tpred) MQ_CUDA(d2h(tpred, h->tpred + (size_t)chain * h->np, h->np, h->stream));
     MQ_CUDA(cudaStreamSynchronize(h->stream));
     return check_device_errors(h);
+}
+
+extern "C" int mq_profile(mq_handle* hh, int enable, double* eikonal_ms, int64_t* eikonal_launches, int64_t* solves_per_full_launch)
+{
+    if (!hh) { set_error("mq_profile: null"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    MQ_CUDA(cudaSetDevice(h->device));
+    double ms = 0;
+    long n = 0;
+    profile_collect(h, &ms, &n, enable != 0);
+    profile_enable(h, enable != 0);
+    if (eikonal_ms) *eikonal_ms = ms;
+    if (eikonal_launches) *eikonal_launches = n;
+    if (solves_per_full_launch) *solves_per_full_launch = (int64_t)2 * h->n * h->nz;
+    return MQ_OK;
+}
+
+// ---- device timers on the handle's stream (bench.py times K steps with these) ---------------------
+static cudaEvent_t g_timer_ev[2][16];
+extern "C" int mq_timer(mq_handle* hh, int slot, int stop, double* elapsed_ms)
+{
+    if (!hh || slot < 0 || slot >= 16) { set_error("mq_timer: bad argument"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    MQ_CUDA(cudaSetDevice(h->device));
+    cudaEvent_t& e = g_timer_ev[stop ? 1 : 0][slot];
+    if (!e) MQ_CUDA(cudaEventCreate(&e));
+    MQ_CUDA(cudaEventRecord(e, h->stream));
+    if (stop) {
+        MQ_CUDA(cudaEventSynchronize(e));
+        float ms = 0.f;
+        if (!g_timer_ev[0][slot]) { set_error("mq_timer: stop without start"); return MQ_ERR_STATE; }
+        MQ_CUDA(cudaEventElapsedTime(&ms, g_timer_ev[0][slot], e));
+        if (elapsed_ms) *elapsed_ms = ms;
+    }
+    return MQ_OK;
 }

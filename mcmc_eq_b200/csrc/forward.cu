@@ -7,6 +7,8 @@
 #include "eikonal.cuh"
 #include "launch_count.h"
 
+#include <vector>
+
 namespace mq {
 
 // ---- work list for "all chains" ---------------------------------------------------------
@@ -73,8 +75,55 @@ cudaError_t launch_rasterise(Handle* h, const EvalView& v, int max_items)
     return cudaGetLastError();
 }
 
+// ---- timing of the eikonal launches (mq_profile) -------------------------------------------
+struct Profile {
+    std::vector<cudaEvent_t> ev;   // start/stop pairs not yet read
+    double ms_total = 0;
+    long launches = 0;
+    bool enabled = false;
+};
+
+void profile_enable(Handle* h, bool on)
+{
+    if (!h->prof) h->prof = new Profile();
+    ((Profile*)h->prof)->enabled = on;
+}
+void profile_collect(Handle* h, double* ms, long* launches, bool reset)
+{
+    Profile* p = (Profile*)h->prof;
+    if (!p) { *ms = 0; *launches = 0; return; }
+    for (size_t i = 0; i + 1 < p->ev.size(); i += 2) {
+        float t = 0.f;
+        cudaEventSynchronize(p->ev[i + 1]);
+        cudaEventElapsedTime(&t, p->ev[i], p->ev[i + 1]);
+        p->ms_total += t;
+        p->launches++;
+        cudaEventDestroy(p->ev[i]);
+        cudaEventDestroy(p->ev[i + 1]);
+    }
+    p->ev.clear();
+    *ms = p->ms_total;
+    *launches = p->launches;
+    if (reset) { p->ms_total = 0; p->launches = 0; }
+}
+void profile_destroy(Handle* h)
+{
+    double a; long b;
+    if (h->prof) { profile_collect(h, &a, &b, true); delete (Profile*)h->prof; h->prof = nullptr; }
+}
+
 cudaError_t launch_tables(Handle* h, int max_items)
 {
+    Profile* pr = (Profile*)h->prof;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (pr && pr->enabled) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, h->stream);
+    }
+    struct Stop {
+        Profile* pr; cudaEvent_t e0, e1; cudaStream_t s;
+        ~Stop() { if (e0) { cudaEventRecord(e1, s); pr->ev.push_back(e0); pr->ev.push_back(e1); } }
+    } stop{pr, e0, e1, h->stream};
     EikBatch b = {};
     b.nxmod = h->nxmod; b.nz = h->nz;
     b.slow = h->slow; b.n_items = max_items; b.n_items_dev = h->n_items;

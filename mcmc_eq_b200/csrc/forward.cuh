@@ -15,4 +15,9 @@ cudaError_t launch_misfit(Handle* h, const EvalView& v);
 // per-chain class sums mf_eval[c][8] from the per-event sums of the view
 cudaError_t launch_totals(Handle* h, const EvalView& v);
 
+// CUDA-event timing of the eikonal launches (mq_profile)
+void profile_enable(Handle* h, bool on);
+void profile_collect(Handle* h, double* ms, long* launches, bool reset);
+void profile_destroy(Handle* h);
+
 }  // namespace mq

@@ -95,6 +95,9 @@ struct Handle {
 
     // sampler (chain.cu)
     void* sampler;
+
+    // optional timing of the dominant kernel (mq_profile): CUDA events round every eikonal launch
+    void* prof;
 };
 
 }  // namespace mq
