@@ -431,7 +431,7 @@ extern "C" int mq_get_table(mq_handle* hh, int chain, int phase, float* ttt)
     EikBatch b = {};
     b.nxmod = nx; b.nz = nz; b.slow = d_slow; b.n_items = nz; b.src_iz = d_iz; b.n_solves = nz;
     b.full_out = d_out; b.status_min = h->solve_status; b.scratch = h->scratch; b.max_warps = h->scratch_warps;
-    MQ_CUDA(eik_launch_generic(b, s));
+    MQ_CUDA(eik_launch(b, s));
     std::vector<float> t((size_t)nz * nodes);
     MQ_CUDA(d2h(t.data(), d_out, t.size(), s));
     MQ_CUDA(cudaStreamSynchronize(s));

@@ -65,7 +65,7 @@ extern "C" int mq_eikonal_batch(const float* slow, const int32_t* src_iz, int n,
         EikBatch b = {};
         b.nxmod = nxmod; b.nz = nz; b.slow = d_slow; b.n_items = m; b.src_iz = d_iz; b.n_solves = m;
         b.full_out = d_out; b.status = d_st; b.scratch = d_scr; b.max_warps = max_warps;
-        TRY(eik_launch_generic(b, 0));
+        TRY(eik_launch(b, 0));
         TRY(cudaDeviceSynchronize());
         TRY(cudaMemcpy(t_out + (size_t)off * nodes, d_out, (size_t)m * nodes * sizeof(float), cudaMemcpyDeviceToHost));
         std::vector<int32_t> st(m);

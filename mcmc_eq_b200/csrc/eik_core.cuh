@@ -360,10 +360,12 @@ EIK_HD void refine_axis(int s_coarse, int n_coarse, int* n, int* src, int* c0, i
     if ((d = s_coarse + kInitMin - n_coarse + 1) >= 0) *n -= 1 + 2 * d;
 }
 
-// Initialisation round the source (reference init_point, src/time_2d.c:503-717) minus the
-// re-discretised branch.  Returns true when the re-discretised initialisation is required.
+// Initialisation round the source (reference init_point, src/time_2d.c:503-717), in two steps.
+// seed_search: the largest quasi-homogeneous box round the source and what to do with it.
+enum SeedKind : int { kSeedBox = 0, kSeedNearest = 1, kSeedRefine = 2 };
+
 template <class G>
-EIK_HD bool seed_source(G& g, bool allow_refine)
+EIK_HD int seed_search(G& g, bool allow_refine)
 {
     const int mx = g.mx, my = g.my, ys = g.ys;
     const int ysc = (ys == my) ? ys - 1 : ys;
@@ -393,34 +395,56 @@ EIK_HD bool seed_source(G& g, bool allow_refine)
     if (failS) Y1--;
     if (Y0 > ys || Y1 < ys) { Y0 = ysc; X1 = 1; Y1 = ysc + 1; }   // X1 >= 1 > xs = 0 always
     g.X1 = X1; g.Y0 = Y0; g.Y1 = Y1;
-
     if (!allow_refine ||
-        ((Y0 == 0 || (ys - Y0) >= kInitMin) && (X1 == mx || X1 >= kInitMin) && (Y1 == my || (Y1 - ys) >= kInitMin))) {
-        if (X1 * (Y1 - Y0) == 1) {
-            // reference init_nearest for a node source on the left edge (:733-739)
-            EIK_CNT(g, nearest_init);
-            if (0 < mx && ys < my) seed_cell(g, 0, 0, 0, ys);
-            if (0 < mx && ys) seed_cell(g, 0, 1, 0, ys - 1);
-        } else {
-            EIK_CNT(g, box_init);
-            for (int x = 0; x <= X1; x++)
-                for (int y = Y0; y <= Y1; y++) {
-                    const float fy = (float)(y - ys);
-                    const float sq = fmaf((float)x, (float)x, fy * fy);   // exact: small integers
-                    float s = sqrtf(sq);
+        ((Y0 == 0 || (ys - Y0) >= kInitMin) && (X1 == mx || X1 >= kInitMin) && (Y1 == my || (Y1 - ys) >= kInitMin)))
+        return (X1 * (Y1 - Y0) == 1) ? kSeedNearest : kSeedBox;
+    return kSeedRefine;
+}
+
+// exact time of node (x,y) in the homogeneous box round the source (src/time_2d.c:695-699)
+EIK_HD float box_time(float hs0, int x, int dy)
+{
+    const float fy = (float)dy;
+    const float sq = fmaf((float)x, (float)x, fy * fy);   // exact: small integers
+    const float s = sqrtf(sq);
 #ifdef EIK_COMPENSATED
-                    if (s > 0.f) {
-                        const float c = fmaf(-s, s, sq) * (0.5f / s);
-                        g.T(x, y) = fmaf(hs0, s, hs0 * c);
-                        continue;
-                    }
-#endif
-                    g.T(x, y) = hs0 * s;
-                }
-        }
-        return false;
+    if (s > 0.f) {
+        const float c = fmaf(-s, s, sq) * (0.5f / s);
+        return fmaf(hs0, s, hs0 * c);
     }
-    return true;
+#endif
+    return hs0 * s;
+}
+
+template <class G>
+EIK_HD float source_slowness(const G& g) { return g.S(0, (g.ys == g.my) ? g.ys - 1 : g.ys); }
+
+// seed_fill: times of the box found by seed_search (kinds kSeedBox and kSeedNearest).
+template <class G>
+EIK_HD void seed_fill(G& g, int kind)
+{
+    const int ys = g.ys;
+    if (kind == kSeedNearest) {
+        // reference init_nearest for a node source on the left edge (:733-739)
+        EIK_CNT(g, nearest_init);
+        if (0 < g.mx && ys < g.my) seed_cell(g, 0, 0, 0, ys);
+        if (0 < g.mx && ys) seed_cell(g, 0, 1, 0, ys - 1);
+    } else {
+        EIK_CNT(g, box_init);
+        const float hs0 = source_slowness(g);
+        for (int x = 0; x <= g.X1; x++)
+            for (int y = g.Y0; y <= g.Y1; y++) g.T(x, y) = box_time(hs0, x, y - ys);
+    }
+}
+
+// Returns true when the re-discretised initialisation is required.
+template <class G>
+EIK_HD bool seed_source(G& g, bool allow_refine)
+{
+    const int kind = seed_search(g, allow_refine);
+    if (kind == kSeedRefine) return true;
+    seed_fill(g, kind);
+    return false;
 }
 
 // Complete solve of one source.  `t` must hold nx*ny nodes, `tf` (kFineMax*22 nodes is

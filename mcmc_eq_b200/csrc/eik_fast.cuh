@@ -1,0 +1,475 @@
+// eik_fast.cuh -- warp-synchronous Podvin-Lecomte solver: 32 solves per warp, the live part of
+// every time field in shared memory, one node update per lane and iteration.
+//
+// What is kept from the generic solver (eik_core.cuh): the arithmetic of every stencil and the
+// visiting order inside a solve (reference src/time_2d.c:959-1147, 1186-1373), hence the results.
+// What is different:
+//   * The expanding box only ever reads its own perimeter: the top row, the bottom row and the
+//     right column (the source sits on the left edge, X0 == 0).  Those three lines live in shared
+//     memory, lane-interleaved ([index][lane], bank == lane: conflict-free whatever index a lane
+//     is at), and a side sweep overwrites the past line IN PLACE with the new one: the values the
+//     stencils still need (past and current time at the previous node of the walk) are carried in
+//     registers, the one node a later walk revisits (the local maximum between two minima) keeps
+//     its past value in a register.
+//   * After the box spans the full depth range the solve is a pure march over columns with a
+//     working set of ONE column per lane; receiver rows are emitted as the march passes.
+//   * All lanes of a warp run the same instruction stream: the per-lane walk position and
+//     direction are data.  Lanes are grouped by source depth, so their boxes grow in step.
+//   * Head waves along a row (a faster layer on the far side, src/time_2d.c:1029-1059) are
+//     detected, not handled, by the fast sweep: the lane re-does that line with the generic
+//     sweep (eik_core.cuh) on the global-memory copy of the box that every fast sweep writes
+//     through to, including the reverse propagation, and reloads its perimeter.  The same slow
+//     path takes the few other irregular cases (exact ties on a plateau, pre-set nodes after the
+//     minimal initialisation, boxes that touch the right edge).
+//
+// Compiles for the device and, with a 1-lane "warp", for the host (tests/emu) bit-identically.
+#pragma once
+#include "eik_core.cuh"
+
+namespace eikf {
+
+using eik::kInf;
+using eik::kFuzz;
+using eik::kInitMin;
+using eik::kRsqrt2;
+using eik::kSqrt2;
+
+#ifdef __CUDA_ARCH__
+constexpr int LS = 32;   // lane stride of the interleaved arrays
+#define EIKF_ANY(p) __any_sync(0xffffffffu, (p))
+#define EIKF_SYNC() __syncwarp()
+#else
+constexpr int LS = 1;
+#define EIKF_ANY(p) (p)
+#define EIKF_SYNC() ((void)0)
+#endif
+
+struct Dims {
+    int nx, nz;          // coarse plane
+    int wx;              // columns of the global box window: min(nx, max(nz + 3, 13))
+    int col_len;         // floats per lane of the column buffer  (>= max(nz, 43))
+    int row_len;         // floats per lane of the row buffer     (>= max(nz + 8, 48))
+};
+
+// One lane's view of the storage.
+struct Lane {
+    float* S;      // shared: slowness per coarse depth cell, S[my] = INF (masked dummy row)
+    float* COL;    // shared: right column of the box, in place
+    float* ROW;    // shared: top row at [x], bottom row at [row_len-1-x]
+    float* W;      // global: coarse box window, node (x,y) at W[(x*nz+y)*LS]
+    float* WF;     // global: refined grid, node (x,y) at WF[(x*nyf+y)*LS]
+};
+
+// Medium of the grid being solved, for the fast sweeps: depth cells come from the shared array
+// either directly (coarse) or through the half-spacing map (refined, src/time_2d.c:865-871).
+struct Med {
+    const float* S;
+    int fine, j0, hy;
+    EIK_HD float cell(int cy) const
+    {
+        return fine ? 0.5f * S[(size_t)(j0 + ((cy + hy) >> 1)) * LS] : S[(size_t)cy * LS];
+    }
+};
+
+// Box state of one lane on one grid.
+struct Box {
+    int nx, ny, mx, my;   // this grid
+    int ys;               // source (0, ys)
+    int X1, Y0, Y1;
+    int preset_up;        // row above the box holds pre-set nodes (minimal initialisation)
+    int active;
+};
+
+// ---- one node of a walk ------------------------------------------------------------------------
+// pk: past time at the node, pn/cn: past and current time at the neighbour towards the minimum,
+// c: current value of the node so far, hs0: cell between node and neighbour, hs1: next cell away
+// from the minimum (use3 == false where the reference has no such cell: k == 0 walking backwards).
+EIK_HD float node_update(float c, float pk, float pn, float cn, float hs0, float hs1, bool use3)
+{
+    const float lim = hs0 * kRsqrt2;
+    const float hs0sq = hs0 * hs0;
+    const float dt = pk - pn;
+    float est = eik::add_sqrt(pk, fmaf(-dt, dt, hs0sq));          // plane wave through the past side
+    est = (dt < lim) ? est : kInf;
+    c = (est < c) ? est : c;
+    const float dt2 = cn - pn;
+    est = eik::add_sqrt(cn, fmaf(-dt2, dt2, hs0sq));              // plane wave through the lateral side
+    est = (dt2 >= 0.f && dt2 < lim) ? est : kInf;
+    c = (est < c) ? est : c;
+    est = use3 ? pk + hs1 : kInf;                                 // 1-D transmission towards the future
+    c = (est < c) ? est : c;
+    est = fmaf(hs0, kSqrt2, pn);                                  // corner diffraction
+    c = (est < c) ? est : c;
+    return c;
+}
+
+// Would the head-wave stencil of src/time_2d.c:1029-1059 change anything at this node?
+EIK_HD bool headwave_fires(float c, float cn, float hs2)
+{
+    float est = cn + hs2;
+    if ((c - est) > kFuzz * c) return true;
+    est = c + hs2;
+    return (cn - est) > kFuzz * cn;
+}
+
+// ---- fast sweep of one line -----------------------------------------------------------------------------
+// P: the past line, C: where the new line goes (element k at X[k*stride]).  Two storage disciplines:
+//   in place (C == P, inplace = true): the line is overwritten as the walk passes; the one node a later
+//     walk revisits (the local maximum between two minima) keeps its past value in a register.  A walk that
+//     would have to go further back over overwritten values (an exact tie there) gives up -> slow path.
+//   ping-pong (C != P): nothing is lost, every case of the reference's walk is reproduced; used on the
+//     march, where no global copy exists to fall back on.
+// ROW sweeps have a constant strip slowness c (and far-side slowness c2 for the head-wave test); COL
+// sweeps read the strip slowness per depth cell from `med`.
+// Wt/wstride: write-through target of node k (Wt[k*wstride]), or nullptr.
+// Returns true for lanes that must re-do the line on the slow path.
+template <bool ROW>
+EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inplace, int kb, int ke, const Med& med,
+                       float c, float c2, float* Wt, long wstride)
+{
+    bool slow = false;
+    const bool hw = ROW && (c2 < c);
+    int k = kb;
+    int vhi = kb - 1;      // nodes kb..vhi of the new line have been written
+    float plast = 0.f;     // past-line time of node vhi (in-place discipline)
+    bool eq_tail = false;  // the last forward walk ended on an exact tie
+
+    while (EIKF_ANY(act && !slow && k <= ke)) {
+        const bool live = act && !slow && k <= ke;
+        // -- next local minimum of the past line
+        float pk = live ? P[(long)k * stride] : 0.f;
+        {
+            bool go = live && k < ke;
+            while (EIKF_ANY(go)) {
+                if (go) {
+                    const float pnx = P[(long)(k + 1) * stride];
+                    if (pnx < pk) { pk = pnx; k++; go = k < ke; }
+                    else go = false;
+                }
+            }
+        }
+        const int kmin = k;
+        const float pmin = pk;
+        float cmin = kInf;
+        if (live) {
+            float hs1, hs0;
+            if (ROW) { hs1 = c; hs0 = (k == 0) ? kInf : c; }
+            else { hs1 = med.cell(k); hs0 = (k == 0) ? kInf : med.cell(k - 1); }
+            const float est = pk + eik::fmin_ref(hs0, hs1);
+            cmin = (est < kInf) ? est : kInf;
+            C[(long)k * stride] = cmin;
+            if (Wt) Wt[(long)k * wstride] = cmin;
+        }
+        // -- walk towards kb
+        {
+            int kk = kmin - 1;
+            float pn = pmin, cn = cmin;
+            bool go = live && kk >= kb;
+            while (EIKF_ANY(go)) {
+                if (go) {
+                    const bool seen = (kk <= vhi);
+                    const float pk2 = (inplace && seen) ? plast : P[(long)kk * stride];
+                    if (pk2 - pn >= 0.f) {
+                        if (inplace && seen && eq_tail) slow = true;   // the walk would go on over overwritten values
+                        const float hs0 = ROW ? c : med.cell(kk);
+                        const float hs1 = ROW ? c : ((kk != 0) ? med.cell(kk - 1) : 0.f);
+                        const float cold = seen ? C[(long)kk * stride] : kInf;
+                        const float cv = node_update(cold, pk2, pn, cn, hs0, hs1, kk != 0);
+                        if (hw && headwave_fires(cv, cn, c2)) slow = true;
+                        C[(long)kk * stride] = cv;
+                        if (Wt) Wt[(long)kk * wstride] = cv;
+                        pn = pk2; cn = cv;
+                        kk--;
+                        go = !slow && !(inplace && seen) && kk >= kb;
+                    } else go = false;
+                }
+            }
+        }
+        // -- walk towards ke
+        if (live && kmin == ke) k = ke + 1;
+        {
+            int kk = kmin + 1;
+            float pn = pmin, cn = cmin;
+            bool go = live && !slow && kmin < ke;
+            if (go) { vhi = kmin; plast = pmin; eq_tail = false; }
+            while (EIKF_ANY(go)) {
+                if (go) {
+                    const float pk2 = P[(long)kk * stride];
+                    const float dt = pk2 - pn;
+                    if (dt >= 0.f) {
+                        const float hs0 = ROW ? c : med.cell(kk - 1);
+                        const float hs1 = ROW ? c : med.cell(kk);
+                        const float cv = node_update(kInf, pk2, pn, cn, hs0, hs1, true);
+                        if (hw && headwave_fires(cv, cn, c2)) slow = true;
+                        C[(long)kk * stride] = cv;
+                        if (Wt) Wt[(long)kk * wstride] = cv;
+                        vhi = kk; plast = pk2; eq_tail = (dt == 0.f);
+                        pn = pk2; cn = cv;
+                        kk++;
+                        go = !slow && kk <= ke;
+                    } else go = false;
+                }
+            }
+            if (live && kmin < ke) k = kk;
+        }
+    }
+    return slow;
+}
+
+// ---- perimeter <-> global window -------------------------------------------------------------------
+template <class G>
+EIK_HD void load_perimeter(const G& g, const Lane& L, int row_len)
+{
+    // a row is only kept while the box can still grow on that side; the two rows share one buffer
+    // (top from the front, bottom from the back) whose length covers them exactly under that rule
+    for (int x = 0; x <= g.X1; x++) {
+        if (g.Y0 > 0) L.ROW[(size_t)x * LS] = g.T(x, g.Y0);
+        if (g.Y1 < g.my) L.ROW[(size_t)(row_len - 1 - x) * LS] = g.T(x, g.Y1);
+    }
+    for (int y = g.Y0; y <= g.Y1; y++) L.COL[(size_t)y * LS] = g.T(g.X1, y);
+}
+
+template <class Medium>
+EIK_HD eik::Grid<Medium> make_grid(float* t, const Box& b, const Medium& m)
+{
+    eik::Grid<Medium> g;
+    g.t = t; g.ts = LS; g.nx = b.nx; g.ny = b.ny; g.mx = b.mx; g.my = b.my; g.S = m; g.ys = b.ys;
+    g.X1 = b.X1; g.Y0 = b.Y0; g.Y1 = b.Y1; g.side_limit = 0; g.status = eik::kOk; g.cnt = nullptr;
+    return g;
+}
+
+// Slow path of one line: the generic sweep (with head waves and reverse propagation) on the global
+// copy, then the perimeter is re-read.  `refill`: the fast sweep already wrote part of the line.
+template <int AXIS, class Medium>
+EIK_HD int slow_line(float* t, const Box& b, const Medium& m, const Lane& L, int row_len, int line, int future,
+                     int kb, int ke, bool refill)
+{
+    eik::Grid<Medium> g = make_grid(t, b, m);
+    if (refill)
+        for (int k = kb; k <= ke; k++) eik::node<AXIS>(g, line, k) = kInf;
+    eik::sweep_line<AXIS>(g, line, future, kb, ke);
+    load_perimeter(g, L, row_len);
+    return g.status;
+}
+
+// ---- expanding box + march on one grid, all lanes of the warp together --------------------------------
+// FINE selects the medium type of the slow path.  out/rows: receiver-row output of the coarse grid
+// (nullptr on the refined grid); out[r*out_rstride + x] receives t[x][rows[r]].
+template <bool FINE>
+EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMedium& cm, int j0, int hy, float* out,
+                    long out_rstride, const int* rows, int n_rows, float* full, int* xbox_end)
+{
+    float* T = FINE ? L.WF : L.W;
+    Med med;
+    med.S = L.S; med.fine = FINE ? 1 : 0; med.j0 = j0; med.hy = hy;
+    const eik::FineMedium fm{cm, j0, hy};
+    int status = eik::kOk;
+    const int RL = D.row_len;
+    const int wx = FINE ? b.nx : D.wx;
+    bool boxphase = b.active && (b.Y0 > 0 || b.Y1 < b.my);
+    float* col = L.COL;      // the lane's current right column
+    float* spare = L.ROW;    // second column buffer, valid once the rows are no longer needed
+    if (xbox_end) *xbox_end = boxphase ? -1 : b.X1;
+    // cell slowness of a row strip, with the masked dummy row of the coarse grid
+    auto rowS = [&](int cy) -> float { return (!FINE && cy >= b.my) ? kInf : med.cell(cy); };
+
+    for (;;) {
+        bool moved = false;
+        // ---- row above the box (reference x_side(Y0, -1), src/time_2d.c:934-939)
+        {
+            const bool need = b.active && b.Y0 > 0;
+            if (EIKF_ANY(need)) {
+                moved = true;
+                int line = 0;
+                bool slow = false, refill = true;
+                if (need) {
+                    line = --b.Y0;
+                    if (b.preset_up || b.X1 >= b.mx) { slow = true; refill = false; }
+                }
+                const float c = need ? rowS(line) : 1.f;
+                const float c2 = (need && line - 1 >= 0) ? rowS(line - 1) : kInf;   // far < 0: no head wave
+                const bool s2 = fast_sweep<true>(need && !slow, L.ROW, L.ROW, LS, true, 0, b.X1, med, c, c2,
+                                                 T + (size_t)line * LS, (long)b.ny * LS);
+                if (need && (slow || s2)) {
+                    const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, -1, 0, b.X1, refill)
+                                        : slow_line<1>(T, b, cm, L, RL, line, -1, 0, b.X1, refill);
+                    if (rc != eik::kOk) status = rc;
+                    b.preset_up = 0;
+                }
+                if (need) col[(size_t)line * LS] = L.ROW[(size_t)b.X1 * LS];
+            }
+        }
+        // ---- column right of the box (reference y_side(X1, +1), src/time_2d.c:940-945)
+        {
+            const bool need = b.active && b.X1 < b.mx;
+            if (EIKF_ANY(need)) {
+                moved = true;
+                int line = 0;
+                if (need) line = ++b.X1;
+                // While the box is growing the column is swept in place (the row buffer is busy and the window
+                // is there to fall back on); on the march it ping-pongs between the column and the idle row buffer.
+                const bool inplace = boxphase;
+                float* dst = inplace ? col : spare;
+                const bool wt = need && (FINE || boxphase) && line < wx;
+                const bool s2 = fast_sweep<false>(need, col, dst, LS, inplace, b.Y0, b.Y1, med, 0.f, 0.f,
+                                                  wt ? T + (size_t)line * b.ny * LS : nullptr, LS);
+                if (need && !inplace) { spare = col; col = dst; }
+                if (need && s2) {   // an exact tie on an in-place column: re-done on the window
+                    const int rc = FINE ? slow_line<0>(T, b, fm, L, RL, line, 1, b.Y0, b.Y1, true)
+                                        : slow_line<0>(T, b, cm, L, RL, line, 1, b.Y0, b.Y1, true);
+                    if (rc != eik::kOk) status = rc;
+                }
+                if (need) {
+                    if (boxphase) {
+                        if (b.Y0 > 0) L.ROW[(size_t)line * LS] = col[(size_t)b.Y0 * LS];
+                        if (b.Y1 < b.my) L.ROW[(size_t)(RL - 1 - line) * LS] = col[(size_t)b.Y1 * LS];
+                    } else {
+                        if (out)
+                            for (int r = 0; r < n_rows; r++) out[(long)r * out_rstride + line] = col[(size_t)rows[r] * LS];
+                        if (full)
+                            for (int y = 0; y < b.ny; y++) full[(size_t)line * b.ny + y] = col[(size_t)y * LS];
+                    }
+                }
+            }
+        }
+        // ---- row below the box (reference x_side(Y1, +1), src/time_2d.c:946-951)
+        {
+            const bool need = b.active && b.Y1 < b.my;
+            if (EIKF_ANY(need)) {
+                moved = true;
+                int line = 0;
+                bool slow = false;
+                if (need) {
+                    line = ++b.Y1;
+                    if (b.X1 >= b.mx) slow = true;
+                }
+                const float c = need ? rowS(line - 1) : 1.f;
+                const float c2 = need ? rowS(line) : kInf;
+                float* bot = L.ROW + (size_t)(RL - 1) * LS;
+                const bool s2 = fast_sweep<true>(need && !slow, bot, bot, -LS, true, 0, b.X1, med, c, c2,
+                                                 T + (size_t)line * LS, (long)b.ny * LS);
+                if (need && (slow || s2)) {
+                    const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, 1, 0, b.X1, !slow)
+                                        : slow_line<1>(T, b, cm, L, RL, line, 1, 0, b.X1, !slow);
+                    if (rc != eik::kOk) status = rc;
+                }
+                if (need) col[(size_t)line * LS] = L.ROW[(size_t)(RL - 1 - b.X1) * LS];
+            }
+        }
+        if (b.active && boxphase && b.Y0 == 0 && b.Y1 == b.my) {
+            boxphase = false;            // from here on the solve is a march over columns
+            if (xbox_end) *xbox_end = b.X1;
+        }
+        if (!EIKF_ANY(moved)) break;
+    }
+    return status;
+}
+
+
+// ---- one warp = up to 32 solves ----------------------------------------------------------------------
+constexpr int kNeedGeneric = 1;   // status: the lane met a case only the generic solver handles
+
+struct LaneTask {
+    bool valid;
+    int iz;
+    const float* slow;   // global: h/v per depth cell of this lane's column, nz values
+    float* out;          // receiver rows: out[r*out_rstride + x] = t[x][rows[r]]  (or nullptr)
+    long out_rstride;
+    float* full;         // whole field in the reference layout x*nz+y (or nullptr)
+};
+
+EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int* rows, int n_rows)
+{
+    const int nx = D.nx, nz = D.nz, mx = nx - 1, my = nz - 1;
+    int status = eik::kOk;
+    // slowness column -> shared, dummy row masked the way the reference masks it (src/time_2d.c:489-492)
+    if (t.valid) {
+        for (int k = 0; k < my; k++) L.S[(size_t)k * LS] = t.slow[k];
+        L.S[(size_t)my * LS] = kInf;
+    }
+    const eik::CoarseMedium cm{L.S, LS, mx, my};
+    Box bc;   // coarse box
+    bc.nx = nx; bc.ny = nz; bc.mx = mx; bc.my = my; bc.ys = t.iz; bc.X1 = 0; bc.Y0 = 0; bc.Y1 = 0; bc.preset_up = 0; bc.active = 0;
+    Box bf = bc;   // refined box
+    int j0 = 0, hy = 0;
+    bool whole = false;
+    float hs0 = 0.f;
+    if (t.valid) {
+        eik::Grid<eik::CoarseMedium> g = make_grid(L.W, bc, cm);
+        const int kind = eik::seed_search(g, true);
+        bc.X1 = g.X1; bc.Y0 = g.Y0; bc.Y1 = g.Y1;
+        hs0 = eik::source_slowness(g);
+        whole = (kind == eik::kSeedBox && g.X1 == mx && g.Y0 == 0 && g.Y1 == my);
+        if (!whole) {
+            const int wn = D.wx * nz;
+            for (int i = 0; i < wn; i++) L.W[(size_t)i * LS] = kInf;
+            bc.active = 1;
+        }
+        if (kind == eik::kSeedRefine) {
+            // geometry of the half-spacing grid (reference recursive_init, src/time_2d.c:844-864)
+            int nxf, nyf, xsf, ysf, i0, hx;
+            eik::refine_axis(0, nx, &nxf, &xsf, &i0, &hx);
+            eik::refine_axis(t.iz, nz, &nyf, &ysf, &j0, &hy);
+            bf.nx = nxf; bf.ny = nyf; bf.mx = nxf - 1; bf.my = nyf - 1; bf.ys = ysf;
+            const eik::FineMedium fm{cm, j0, hy};
+            for (int i = 0; i < nxf * nyf; i++) L.WF[(size_t)i * LS] = kInf;
+            eik::Grid<eik::FineMedium> f = make_grid(L.WF, bf, fm);
+            const int kf = eik::seed_search(f, false);
+            eik::seed_fill(f, kf);
+            bf.X1 = f.X1; bf.Y0 = f.Y0; bf.Y1 = f.Y1;
+            bf.preset_up = (kf == eik::kSeedNearest && ysf > 0 && ysf < bf.my) ? 1 : 0;
+            bf.active = 1;
+            load_perimeter(f, L, D.row_len);
+        } else if (!whole) {
+            eik::seed_fill(g, kind);
+            bc.preset_up = (kind == eik::kSeedNearest && t.iz > 0 && t.iz < my) ? 1 : 0;
+        }
+    }
+    EIKF_SYNC();
+    // ---- refined grids of the lanes that need one
+    if (EIKF_ANY(bf.active)) {
+        const int rc = run_grid<true>(bf, L, D, cm, j0, hy, nullptr, 0, nullptr, 0, nullptr, nullptr);
+        if (rc != eik::kOk) status = rc;
+        if (bf.active) {
+            // every second fine node is a coarse node (src/time_2d.c:887-890); the fine field is complete in WF
+            for (int i = 0, ii = 0; ii < bf.nx; ii += 2, i++)
+                for (int j = j0 + hy, jj = hy; jj < bf.ny; jj += 2, j++)
+                    L.W[((size_t)i * nz + j) * LS] = L.WF[((size_t)ii * bf.ny + jj) * LS];
+            bc.X1 = (kInitMin < mx) ? kInitMin : mx;
+            bc.Y0 = (t.iz - kInitMin > 0) ? t.iz - kInitMin : 0;
+            bc.Y1 = (t.iz + kInitMin < my) ? t.iz + kInitMin : my;
+        }
+    }
+    if (bc.active) {
+        eik::Grid<eik::CoarseMedium> g = make_grid(L.W, bc, cm);
+        load_perimeter(g, L, D.row_len);
+    }
+    EIKF_SYNC();
+    // ---- coarse grids
+    int xbox_end = -1;
+    {
+        const int rc = run_grid<false>(bc, L, D, cm, 0, 0, t.out, t.out_rstride, rows, n_rows, t.full, &xbox_end);
+        if (rc != eik::kOk) status = rc;
+    }
+    // ---- the part of the output that was computed while the box was still growing (it may have been
+    //      re-timed by reverse propagation until the very end of that phase) comes from the window
+    if (t.valid && !whole) {
+        if (t.out)
+            for (int r = 0; r < n_rows; r++)
+                for (int x = 0; x <= xbox_end; x++) t.out[(long)r * t.out_rstride + x] = L.W[((size_t)x * nz + rows[r]) * LS];
+        if (t.full)
+            for (int x = 0; x <= xbox_end; x++)
+                for (int y = 0; y < nz; y++) t.full[(size_t)x * nz + y] = L.W[((size_t)x * nz + y) * LS];
+    }
+    if (t.valid && whole) {   // homogeneous model: the exact solution everywhere, nothing to propagate
+        if (t.out)
+            for (int r = 0; r < n_rows; r++)
+                for (int x = 0; x < nx; x++) t.out[(long)r * t.out_rstride + x] = eik::box_time(hs0, x, rows[r] - t.iz);
+        if (t.full)
+            for (int x = 0; x < nx; x++)
+                for (int y = 0; y < nz; y++) t.full[(size_t)x * nz + y] = eik::box_time(hs0, x, y - t.iz);
+    }
+    return status;
+}
+
+}  // namespace eikf

@@ -41,5 +41,13 @@ constexpr int kFineNodes = 22 * 43;   // refined grid of a left-edge source, src
 size_t eik_scratch_floats_per_warp(int nxmod, int nz);
 // Generic one-lane-per-solve kernel, time field in global memory.
 cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream);
+// Warp-synchronous kernel, live state in shared memory (eik_fast.cuh).  Same EikBatch; its scratch need per warp
+// is smaller (box window + refined grid) so the generic kernel's scratch always suffices.
+bool eik_fast_supported(int nxmod, int nz);
+cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream);
+// Picks the fast kernel when the grid allows it (MCMCEQ_EIKONAL=generic forces the generic one).
+cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream);
+// resident warps the fast kernel can use on this device (for sizing the scratch)
+int eik_fast_max_warps(int nxmod, int nz, int device);
 
 }  // namespace mq

@@ -130,7 +130,7 @@ cudaError_t launch_tables(Handle* h, int max_items)
     b.row_out = h->item_tab; b.rows = h->d_rows; b.n_rows = h->n_rows; b.xpitch = h->xp;
     b.status_min = h->solve_status;
     b.scratch = h->scratch; b.max_warps = h->scratch_warps;
-    return eik_launch_generic(b, h->stream);
+    return eik_launch(b, h->stream);
 }
 
 // ---- travel-time lookup -------------------------------------------------------------------

@@ -16,6 +16,7 @@ def emu():
     from mcmc_eq_b200 import build
     L = C.CDLL(build.build_emu())
     L.emu_time_2d.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, C.POINTER(C.c_int)]
+    L.emu_fast_time_2d.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, C.POINTER(C.c_int), C.c_int, fp]
     return L
 
 
@@ -68,3 +69,34 @@ def test_core_small_and_degenerate_grids(emu, oracle):
             t, r2, _ = _run(emu, s, nx, iz)
             assert r1 == 0 and r2 == 0
             assert (np.abs(t - tref) <= util.eikonal_tol(tref)).all(), (nx, nz, iz)
+
+
+def _run_fast(emu, s, nx, iz, rows):
+    s = util.f32(s)
+    t = np.full((nx, len(s)), -1.0, np.float32)
+    rows = np.ascontiguousarray(rows, np.int32)
+    ro = np.zeros((len(rows), nx), np.float32)
+    rc = emu.emu_fast_time_2d(ptr(s), nx, len(s), iz, ptr(t), rows.ctypes.data_as(C.POINTER(C.c_int)), len(rows), ptr(ro))
+    return t, ro, rc
+
+
+@pytest.mark.parametrize("seed,grid", [(1, None), (2, util.EXAMPLE_GRID), (3, util.EXAMPLE2_GRID)])
+def test_fast_path_is_bit_identical_to_generic_core(emu, seed, grid):
+    """The shared-memory, in-place / ping-pong solver (eik_fast.cuh) visits the nodes in the same order with the
+    same arithmetic as the generic core: identical bits, whole field and receiver rows, every source depth."""
+    rng = np.random.default_rng(seed)
+    for trial in range(10 if grid is None else 3):
+        if grid is None:
+            nx, nz, h, z0 = int(rng.integers(2, 200)), int(rng.integers(2, 70)), 2.0, 0.0
+        else:
+            nx, nz, h, z0 = util.nxmod_of(grid), grid["nz"], grid["h"], grid["z0"]
+        kind = ["posterior", "contrast", "lvz", "gradient"][trial % 4]
+        z, vp, vpvs = util.voronoi_model(rng, int(rng.integers(1, 21)), z0, z0 + (nz - 1) * h, kind)
+        s = util.rasterise_np(z, vp, vpvs, h, z0, nz, 1 + trial % 2)
+        rows = sorted({0, min(1, nz - 1), min(2, nz - 1), nz - 1})
+        for iz in range(nz):
+            t1, rc1, _ = _run(emu, s, nx, iz)
+            t2, ro, rc2 = _run_fast(emu, s, nx, iz, rows)
+            assert rc1 == rc2 == 0, (nx, nz, iz, rc1, rc2)
+            assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), (nx, nz, kind, iz)
+            assert np.array_equal(ro, t1[:, rows].T)
