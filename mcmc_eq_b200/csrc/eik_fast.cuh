@@ -80,6 +80,23 @@ struct Box {
     int active;
 };
 
+// Correctly rounded sqrt for normal positive arguments: the rsqrt + Newton sequence the compiler emits for
+// sqrtf(), without its range check (arguments here are products of slownesses, far from denormal or huge; a
+// non-positive argument only occurs where the stencil is not selected and yields an ignored NaN).
+EIK_HD float sqrt_pos(float r)
+{
+#ifdef __CUDA_ARCH__
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r));
+    const float s = r * y;
+    const float h = 0.5f * y;
+    const float e = fmaf(-s, s, r);
+    return fmaf(e, h, s);
+#else
+    return sqrtf(r);
+#endif
+}
+
 // ---- one node of a walk ------------------------------------------------------------------------
 // pk: past time at the node, pn/cn: past and current time at the neighbour towards the minimum,
 // c: current value of the node so far, hs0: cell between node and neighbour, hs1: next cell away
@@ -89,11 +106,11 @@ EIK_HD float node_update(float c, float pk, float pn, float cn, float hs0, float
     const float lim = hs0 * kRsqrt2;
     const float hs0sq = hs0 * hs0;
     const float dt = pk - pn;
-    float est = eik::add_sqrt(pk, fmaf(-dt, dt, hs0sq));          // plane wave through the past side
+    float est = pk + sqrt_pos(fmaf(-dt, dt, hs0sq));              // plane wave through the past side
     est = (dt < lim) ? est : kInf;
     c = (est < c) ? est : c;
     const float dt2 = cn - pn;
-    est = eik::add_sqrt(cn, fmaf(-dt2, dt2, hs0sq));              // plane wave through the lateral side
+    est = cn + sqrt_pos(fmaf(-dt2, dt2, hs0sq));                  // plane wave through the lateral side
     est = (dt2 >= 0.f && dt2 < lim) ? est : kInf;
     c = (est < c) ? est : c;
     est = use3 ? pk + hs1 : kInf;                                 // 1-D transmission towards the future
@@ -121,98 +138,104 @@ EIK_HD bool headwave_fires(float c, float cn, float hs2)
 //     march, where no global copy exists to fall back on.
 // ROW sweeps have a constant strip slowness c (and far-side slowness c2 for the head-wave test); COL
 // sweeps read the strip slowness per depth cell from `med`.
+// The walk of a lane is ONE loop: a lane is either looking for its next local minimum (SEG) or at a node of
+// its walk, first towards kb (d = -1) then towards ke (d = +1); position and direction are data, so lanes whose
+// minima sit at different depths do not wait for each other.
 // Wt/wstride: write-through target of node k (Wt[k*wstride]), or nullptr.
+// hint (may be nullptr): in: index of the first local minimum of P if known (>= 0); out: the same for C, found
+// as C is written (valid when the next sweep covers the same [kb, ke]: the march), or -1.
 // Returns true for lanes that must re-do the line on the slow path.
 template <bool ROW>
 EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inplace, int kb, int ke, const Med& med,
-                       float c, float c2, float* Wt, long wstride)
+                       float c, float c2, float* Wt, long wstride, int* hint)
 {
-    bool slow = false;
+    enum { SEG = 0, WALK = 1, DONE = 2 };
     const bool hw = ROW && (c2 < c);
-    int k = kb;
+    int st = act ? SEG : DONE;
+    bool slow = false;
+    int k = kb;            // where the search for the next local minimum starts
     int vhi = kb - 1;      // nodes kb..vhi of the new line have been written
+    int kk = 0, d = -1, kmin = kb, nseg = 0;
+    float pmin = 0.f, cmin = 0.f, pn = 0.f, cn = 0.f, s0 = 0.f, sp = 0.f;
     float plast = 0.f;     // past-line time of node vhi (in-place discipline)
     bool eq_tail = false;  // the last forward walk ended on an exact tie
+    int ans_b = 0x7fffffff, ans_f = ke;   // first local minimum of the new line, tracked as it is written
 
-    while (EIKF_ANY(act && !slow && k <= ke)) {
-        const bool live = act && !slow && k <= ke;
-        // -- next local minimum of the past line
-        float pk = live ? P[(long)k * stride] : 0.f;
-        {
-            bool go = live && k < ke;
-            while (EIKF_ANY(go)) {
-                if (go) {
+    while (EIKF_ANY(st != DONE)) {
+        if (st == SEG) {
+            float pk;
+            if (hint && *hint >= 0 && nseg == 0) {
+                k = *hint;
+                pk = P[(long)k * stride];
+            } else {
+                pk = P[(long)k * stride];
+                while (k < ke) {
                     const float pnx = P[(long)(k + 1) * stride];
-                    if (pnx < pk) { pk = pnx; k++; go = k < ke; }
-                    else go = false;
+                    if (!(pnx < pk)) break;
+                    pk = pnx;
+                    k++;
                 }
             }
-        }
-        const int kmin = k;
-        const float pmin = pk;
-        float cmin = kInf;
-        if (live) {
-            float hs1, hs0;
-            if (ROW) { hs1 = c; hs0 = (k == 0) ? kInf : c; }
-            else { hs1 = med.cell(k); hs0 = (k == 0) ? kInf : med.cell(k - 1); }
-            const float est = pk + eik::fmin_ref(hs0, hs1);
+            nseg++;
+            kmin = k;
+            pmin = pk;
+            float sm;
+            if (ROW) { sp = c; sm = (k == 0) ? kInf : c; }
+            else { sp = med.cell(k); sm = (k == 0) ? kInf : med.cell(k - 1); }
+            const float est = pk + eik::fmin_ref(sm, sp);      // 1-D transmission in front of the minimum
             cmin = (est < kInf) ? est : kInf;
             C[(long)k * stride] = cmin;
             if (Wt) Wt[(long)k * wstride] = cmin;
-        }
-        // -- walk towards kb
-        {
-            int kk = kmin - 1;
-            float pn = pmin, cn = cmin;
-            bool go = live && kk >= kb;
-            while (EIKF_ANY(go)) {
-                if (go) {
-                    const bool seen = (kk <= vhi);
-                    const float pk2 = (inplace && seen) ? plast : P[(long)kk * stride];
-                    if (pk2 - pn >= 0.f) {
-                        if (inplace && seen && eq_tail) slow = true;   // the walk would go on over overwritten values
-                        const float hs0 = ROW ? c : med.cell(kk);
-                        const float hs1 = ROW ? c : ((kk != 0) ? med.cell(kk - 1) : 0.f);
-                        const float cold = seen ? C[(long)kk * stride] : kInf;
-                        const float cv = node_update(cold, pk2, pn, cn, hs0, hs1, kk != 0);
-                        if (hw && headwave_fires(cv, cn, c2)) slow = true;
-                        C[(long)kk * stride] = cv;
-                        if (Wt) Wt[(long)kk * wstride] = cv;
-                        pn = pk2; cn = cv;
-                        kk--;
-                        go = !slow && !(inplace && seen) && kk >= kb;
-                    } else go = false;
+            kk = kmin - 1; d = -1; pn = pmin; cn = cmin; s0 = sm;
+            st = WALK;
+        } else if (st == WALK) {
+            bool ok = (d < 0) ? (kk >= kb) : (kk <= ke);
+            bool seen = false;
+            float pk2 = 0.f;
+            if (ok) {
+                seen = kk <= vhi;
+                pk2 = (inplace && seen) ? plast : P[(long)kk * stride];
+                ok = (pk2 - pn >= 0.f);
+            }
+            if (!ok) {
+                if (d < 0 && kmin < ke) {       // turn round: walk towards ke from the minimum
+                    d = 1; kk = kmin + 1; pn = pmin; cn = cmin; s0 = sp;
+                    vhi = kmin; plast = pmin; eq_tail = false;
+                    seen = false;
+                    pk2 = P[(long)kk * stride];
+                    ok = (pk2 - pn >= 0.f);
+                    if (!ok) { k = kk; st = SEG; }
+                } else if (d < 0) {
+                    st = DONE;                  // the minimum was the last node of the line
+                } else {                        // this segment is finished
+                    k = kk;
+                    st = (k <= ke) ? SEG : DONE;
                 }
             }
-        }
-        // -- walk towards ke
-        if (live && kmin == ke) k = ke + 1;
-        {
-            int kk = kmin + 1;
-            float pn = pmin, cn = cmin;
-            bool go = live && !slow && kmin < ke;
-            if (go) { vhi = kmin; plast = pmin; eq_tail = false; }
-            while (EIKF_ANY(go)) {
-                if (go) {
-                    const float pk2 = P[(long)kk * stride];
-                    const float dt = pk2 - pn;
-                    if (dt >= 0.f) {
-                        const float hs0 = ROW ? c : med.cell(kk - 1);
-                        const float hs1 = ROW ? c : med.cell(kk);
-                        const float cv = node_update(kInf, pk2, pn, cn, hs0, hs1, true);
-                        if (hw && headwave_fires(cv, cn, c2)) slow = true;
-                        C[(long)kk * stride] = cv;
-                        if (Wt) Wt[(long)kk * wstride] = cv;
-                        vhi = kk; plast = pk2; eq_tail = (dt == 0.f);
-                        pn = pk2; cn = cv;
-                        kk++;
-                        go = !slow && kk <= ke;
-                    } else go = false;
+            if (ok) {
+                if (inplace && seen && eq_tail) slow = true;   // the walk would go on over overwritten values
+                const bool use3 = (d > 0) || (kk != 0);
+                float hs0, hs1;
+                if (ROW) { hs0 = c; hs1 = c; }
+                else { hs0 = s0; hs1 = use3 ? med.cell((d > 0) ? kk : kk - 1) : 0.f; }
+                const float cold = seen ? C[(long)kk * stride] : kInf;
+                const float cv = node_update(cold, pk2, pn, cn, hs0, hs1, use3);
+                if (hw && headwave_fires(cv, cn, c2)) slow = true;
+                C[(long)kk * stride] = cv;
+                if (Wt) Wt[(long)kk * wstride] = cv;
+                if (d < 0) { if (cn >= cv) ans_b = kk; }
+                else {
+                    if (cv >= cn && kk - 1 < ans_f) ans_f = kk - 1;
+                    vhi = kk; plast = pk2; eq_tail = (pk2 - pn == 0.f);
                 }
+                pn = pk2; cn = cv; s0 = hs1;
+                kk += d;
+                if (d < 0 && inplace && seen) kk = kb - 1;   // an in-place walk stops after the node it revisits
+                if (slow) st = DONE;
             }
-            if (live && kmin < ke) k = kk;
         }
     }
+    if (hint) *hint = (nseg == 1 && !slow) ? ((ans_b != 0x7fffffff) ? ans_b : ans_f) : -1;
     return slow;
 }
 
@@ -269,6 +292,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
     bool boxphase = b.active && (b.Y0 > 0 || b.Y1 < b.my);
     float* col = L.COL;      // the lane's current right column
     float* spare = L.ROW;    // second column buffer, valid once the rows are no longer needed
+    int hint = -1;           // first local minimum of the current column (known on the march)
     if (xbox_end) *xbox_end = boxphase ? -1 : b.X1;
     // cell slowness of a row strip, with the masked dummy row of the coarse grid
     auto rowS = [&](int cy) -> float { return (!FINE && cy >= b.my) ? kInf : med.cell(cy); };
@@ -289,7 +313,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 const float c = need ? rowS(line) : 1.f;
                 const float c2 = (need && line - 1 >= 0) ? rowS(line - 1) : kInf;   // far < 0: no head wave
                 const bool s2 = fast_sweep<true>(need && !slow, L.ROW, L.ROW, LS, true, 0, b.X1, med, c, c2,
-                                                 T + (size_t)line * LS, (long)b.ny * LS);
+                                                 T + (size_t)line * LS, (long)b.ny * LS, nullptr);
                 if (need && (slow || s2)) {
                     const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, -1, 0, b.X1, refill)
                                         : slow_line<1>(T, b, cm, L, RL, line, -1, 0, b.X1, refill);
@@ -312,7 +336,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 float* dst = inplace ? col : spare;
                 const bool wt = need && (FINE || boxphase) && line < wx;
                 const bool s2 = fast_sweep<false>(need, col, dst, LS, inplace, b.Y0, b.Y1, med, 0.f, 0.f,
-                                                  wt ? T + (size_t)line * b.ny * LS : nullptr, LS);
+                                                  wt ? T + (size_t)line * b.ny * LS : nullptr, LS, inplace ? nullptr : &hint);
                 if (need && !inplace) { spare = col; col = dst; }
                 if (need && s2) {   // an exact tie on an in-place column: re-done on the window
                     const int rc = FINE ? slow_line<0>(T, b, fm, L, RL, line, 1, b.Y0, b.Y1, true)
@@ -347,7 +371,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 const float c2 = need ? rowS(line) : kInf;
                 float* bot = L.ROW + (size_t)(RL - 1) * LS;
                 const bool s2 = fast_sweep<true>(need && !slow, bot, bot, -LS, true, 0, b.X1, med, c, c2,
-                                                 T + (size_t)line * LS, (long)b.ny * LS);
+                                                 T + (size_t)line * LS, (long)b.ny * LS, nullptr);
                 if (need && (slow || s2)) {
                     const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, 1, 0, b.X1, !slow)
                                         : slow_line<1>(T, b, cm, L, RL, line, 1, 0, b.X1, !slow);
