@@ -47,13 +47,27 @@ constexpr int LS = 1;
 struct Dims {
     int nx, nz;          // coarse plane
     int wx;              // columns of the global box window: min(nx, max(nz + 3, 13))
-    int col_len;         // floats per lane of the column buffer  (>= max(nz, 43))
-    int row_len;         // floats per lane of the row buffer     (>= max(nz + 8, 48))
+    int col_len;         // column buffer: indices -1 .. col_len (col_len >= max(nz, 43); -1 and nz hold sentinels)
+    int row_len;         // row buffer: top row from the front, bottom row from the back, never more than
+                         // nz + 3 nodes between them while both are needed; >= max(nz + 4, 48)
 };
+
+EIK_HD Dims make_dims(int nx, int nz)
+{
+    Dims D;
+    D.nx = nx; D.nz = nz;
+    D.wx = (nz + 3 > 13) ? nz + 3 : 13;
+    if (D.wx > nx) D.wx = nx;
+    D.col_len = nz > 43 ? nz : 43;
+    D.row_len = (nz + 4 > 48) ? nz + 4 : 48;
+    return D;
+}
+// floats per lane of the three shared arrays: S[-1..nz-1], COL[-1..col_len], ROW[0..row_len-1]
+EIK_HD int smem_floats_per_lane(const Dims& D) { return (D.nz + 1) + (D.col_len + 2) + D.row_len; }
 
 // One lane's view of the storage.
 struct Lane {
-    float* S;      // shared: slowness per coarse depth cell, S[my] = INF (masked dummy row)
+    float* S;      // shared: slowness per coarse depth cell, S[my] = INF (masked dummy row), S[-1] = INF
     float* COL;    // shared: right column of the box, in place
     float* ROW;    // shared: top row at [x], bottom row at [row_len-1-x]
     float* W;      // global: coarse box window, node (x,y) at W[(x*nz+y)*LS]
@@ -101,22 +115,20 @@ EIK_HD float sqrt_pos(float r)
 // pk: past time at the node, pn/cn: past and current time at the neighbour towards the minimum,
 // c: current value of the node so far, hs0: cell between node and neighbour, hs1: next cell away
 // from the minimum (use3 == false where the reference has no such cell: k == 0 walking backwards).
+// All candidates are finite or INF when they reach fminf (never NaN: an unselected stencil is replaced by INF
+// first), so fminf == the reference's "if (est < t) t = est".
 EIK_HD float node_update(float c, float pk, float pn, float cn, float hs0, float hs1, bool use3)
 {
     const float lim = hs0 * kRsqrt2;
     const float hs0sq = hs0 * hs0;
     const float dt = pk - pn;
     float est = pk + sqrt_pos(fmaf(-dt, dt, hs0sq));              // plane wave through the past side
-    est = (dt < lim) ? est : kInf;
-    c = (est < c) ? est : c;
+    c = fminf(c, (dt < lim) ? est : kInf);
     const float dt2 = cn - pn;
     est = cn + sqrt_pos(fmaf(-dt2, dt2, hs0sq));                  // plane wave through the lateral side
-    est = (dt2 >= 0.f && dt2 < lim) ? est : kInf;
-    c = (est < c) ? est : c;
-    est = use3 ? pk + hs1 : kInf;                                 // 1-D transmission towards the future
-    c = (est < c) ? est : c;
-    est = fmaf(hs0, kSqrt2, pn);                                  // corner diffraction
-    c = (est < c) ? est : c;
+    c = fminf(c, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+    c = fminf(c, use3 ? pk + hs1 : kInf);                         // 1-D transmission towards the future
+    c = fminf(c, fmaf(hs0, kSqrt2, pn));                          // corner diffraction
     return c;
 }
 
@@ -239,6 +251,100 @@ EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inpl
     return slow;
 }
 
+// ---- the march: one full-depth column from the previous one ------------------------------------------------
+// The same walk as fast_sweep<false> in its ping-pong discipline, specialised for the steady state of a solve
+// (kb = 0, ke = my, coarse medium, no write-through, no slow path).  P and C have indices -1 .. ke+1 whose two
+// end slots hold kStop, so a walk ends at the array ends by the very test that ends it at a local maximum of the
+// past column; S[-1] = S[ke] = INF stand for the cells the reference does not look at.
+constexpr float kStop = -1.0e30f;
+
+EIK_HD void march_sweep(bool act, const float* P, float* C, const float* S, int ke, int* hint)
+{
+    bool alive = act;
+    int k = 0, kk = 0, d = -1, kmin = 0, vhi = -1, nseg = 0;
+    float pmin = 0.f, cmin = 0.f, pn = 0.f, cn = 0.f, s0 = 0.f, sp = 0.f;
+    // first local minimum of the new column, tracked as it is written; rv_lo = lowest node a later walk re-timed
+    int ans_b = 0x7fffffff, ans_f = ke, rv_lo = 0x7fffffff;
+
+    auto start_segment = [&](bool use_hint) {
+        float pk;
+        if (use_hint) {
+            k = *hint;
+            pk = P[(long)k * LS];
+        } else {
+            pk = P[(long)k * LS];
+            while (k < ke) {
+                const float pnx = P[(long)(k + 1) * LS];
+                if (!(pnx < pk)) break;
+                pk = pnx;
+                k++;
+            }
+        }
+        nseg++;
+        kmin = k;
+        pmin = pk;
+        sp = S[(long)k * LS];
+        const float sm = S[(long)(k - 1) * LS];
+        cmin = fminf(kInf, pk + eik::fmin_ref(sm, sp));   // 1-D transmission in front of the minimum
+        C[(long)k * LS] = cmin;
+        kk = kmin - 1; d = -1; pn = pmin; cn = cmin; s0 = sm;
+    };
+
+    if (alive) start_segment(*hint >= 0);
+    while (EIKF_ANY(alive)) {
+        if (alive) {
+            float pk2 = P[(long)kk * LS];
+            float dt = pk2 - pn;
+            bool go = true;
+            if (dt < 0.f) {
+                if (d < 0) {                         // the walk towards the top is over: turn round at the minimum
+                    if (kmin == ke) { alive = false; go = false; }
+                    else {
+                        d = 1; kk = kmin + 1; pn = pmin; cn = cmin; s0 = sp; vhi = kmin;
+                        pk2 = P[(long)kk * LS];
+                        dt = pk2 - pn;
+                    }
+                }
+                if (alive && dt < 0.f) {             // the segment is over: next local minimum, or done
+                    go = false;
+                    k = kk;
+                    if (k > ke) alive = false;
+                    else start_segment(false);
+                }
+            }
+            if (go) {
+                const float hs1 = S[(long)((d > 0) ? kk : kk - 1) * LS];
+                float cold = kInf;
+                if (kk <= vhi) {                     // a later walk comes back over nodes already timed
+                    cold = C[(long)kk * LS];
+                    rv_lo = (kk < rv_lo) ? kk : rv_lo;
+                }
+                const float lim = s0 * kRsqrt2;
+                const float s0sq = s0 * s0;
+                float est = pk2 + sqrt_pos(fmaf(-dt, dt, s0sq));
+                float cv = fminf(cold, (dt < lim) ? est : kInf);
+                const float dt2 = cn - pn;
+                est = cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
+                cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+                cv = fminf(cv, pk2 + hs1);
+                cv = fminf(cv, fmaf(s0, kSqrt2, pn));
+                C[(long)kk * LS] = cv;
+                if (d < 0) { if (cn >= cv && kk < ans_b) ans_b = kk; }
+                else {
+                    if (cv >= cn && kk - 1 < ans_f) ans_f = kk - 1;
+                    vhi = kk;
+                }
+                pn = pk2; cn = cv; s0 = hs1;
+                kk += d;
+            }
+        }
+    }
+    if (act) {
+        const int first = (ans_b != 0x7fffffff) ? ans_b : ans_f;
+        *hint = (first + 1 < rv_lo) ? first : -1;
+    }
+}
+
 // ---- perimeter <-> global window -------------------------------------------------------------------
 template <class G>
 EIK_HD void load_perimeter(const G& g, const Lane& L, int row_len)
@@ -291,7 +397,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
     const int wx = FINE ? b.nx : D.wx;
     bool boxphase = b.active && (b.Y0 > 0 || b.Y1 < b.my);
     float* col = L.COL;      // the lane's current right column
-    float* spare = L.ROW;    // second column buffer, valid once the rows are no longer needed
+    float* spare = L.ROW + LS;   // second column buffer (indices -1..ny), valid once the rows are no longer needed
     int hint = -1;           // first local minimum of the current column (known on the march)
     if (xbox_end) *xbox_end = boxphase ? -1 : b.X1;
     // cell slowness of a row strip, with the masked dummy row of the coarse grid
@@ -299,6 +405,34 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
 
     for (;;) {
         bool moved = false;
+        if (!FINE && !EIKF_ANY(b.active && boxphase)) {
+            // ---- every lane of the warp is on the march: one full-depth column per iteration
+            int rr[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) rr[r] = (out && r < n_rows) ? rows[r] : 0;
+            if (b.active) {
+                col[-(long)LS] = kStop; col[(size_t)b.ny * LS] = kStop;
+                spare[-(long)LS] = kStop; spare[(size_t)b.ny * LS] = kStop;
+            }
+            while (EIKF_ANY(b.active && b.X1 < b.mx)) {
+                const bool need = b.active && b.X1 < b.mx;
+                int line = 0;
+                if (need) line = ++b.X1;
+                march_sweep(need, col, spare, L.S, b.my, &hint);
+                if (need) {
+                    float* tmp = col; col = spare; spare = tmp;
+                    if (out) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++)
+                            if (r < n_rows) out[(long)r * out_rstride + line] = col[(size_t)rr[r] * LS];
+                        for (int r = 8; r < n_rows; r++) out[(long)r * out_rstride + line] = col[(size_t)rows[r] * LS];
+                    }
+                    if (full)
+                        for (int y = 0; y < b.ny; y++) full[(size_t)line * b.ny + y] = col[(size_t)y * LS];
+                }
+            }
+            break;
+        }
         // ---- row above the box (reference x_side(Y0, -1), src/time_2d.c:934-939)
         {
             const bool need = b.active && b.Y0 > 0;
@@ -410,6 +544,7 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     if (t.valid) {
         for (int k = 0; k < my; k++) L.S[(size_t)k * LS] = t.slow[k];
         L.S[(size_t)my * LS] = kInf;
+        L.S[-(long)LS] = kInf;     // "cell above the grid": lets the walk drop its k == 0 special cases
     }
     const eik::CoarseMedium cm{L.S, LS, mx, my};
     Box bc;   // coarse box
@@ -494,6 +629,15 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
                 for (int y = 0; y < nz; y++) t.full[(size_t)x * nz + y] = eik::box_time(hs0, x, y - t.iz);
     }
     return status;
+}
+
+
+// lane pointers into a warp's shared-memory slice (base already offset by the lane)
+EIK_HD void carve_shared(float* base, const Dims& D, Lane* L)
+{
+    L->S = base + (size_t)1 * LS;
+    L->COL = L->S + (size_t)D.nz * LS + (size_t)1 * LS;
+    L->ROW = L->COL + (size_t)(D.col_len + 1) * LS;
 }
 
 }  // namespace eikf

@@ -78,17 +78,8 @@ cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream)
 
 
 // ---- warp-synchronous kernel ---------------------------------------------------------------------------
-static eikf::Dims fast_dims(int nxmod, int nz)
-{
-    eikf::Dims D;
-    D.nx = nxmod; D.nz = nz;
-    D.wx = (nz + 3 > 13) ? nz + 3 : 13;
-    if (D.wx > nxmod) D.wx = nxmod;
-    D.col_len = nz > 43 ? nz : 43;
-    D.row_len = (nz + 8 > 48) ? nz + 8 : 48;
-    return D;
-}
-static size_t fast_smem_floats_per_warp(const eikf::Dims& D) { return (size_t)(D.nz + D.col_len + D.row_len) * 32; }
+static eikf::Dims fast_dims(int nxmod, int nz) { return eikf::make_dims(nxmod, nz); }
+static size_t fast_smem_floats_per_warp(const eikf::Dims& D) { return (size_t)eikf::smem_floats_per_lane(D) * 32; }
 static size_t fast_scratch_floats_per_warp(const eikf::Dims& D) { return ((size_t)D.wx * D.nz + kFineNodes) * 32; }
 
 bool eik_fast_supported(int nxmod, int nz)
@@ -105,9 +96,7 @@ __global__ void __launch_bounds__(32) eik_fast_kernel(EikBatch b, eikf::Dims D)
     const int lane = threadIdx.x;
     const int nodes = b.nxmod * b.nz;
     eikf::Lane L;
-    L.S = smem + lane;
-    L.COL = L.S + (size_t)D.nz * 32;
-    L.ROW = L.COL + (size_t)D.col_len * 32;
+    eikf::carve_shared(smem + lane, D, &L);
     L.W = b.scratch + (size_t)blockIdx.x * (((size_t)D.wx * D.nz + kFineNodes) * 32) + lane;
     L.WF = L.W + (size_t)D.wx * D.nz * 32;
     const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;

@@ -20,14 +20,11 @@ extern "C" int emu_time_2d(const float* s, int nx, int ny, int iz, float* t, int
 #include "../../mcmc_eq_b200/csrc/eik_fast.cuh"
 extern "C" int emu_fast_time_2d(const float* s, int nx, int ny, int iz, float* t, const int* rows, int n_rows, float* rows_out)
 {
-    eikf::Dims D;
-    D.nx = nx; D.nz = ny;
-    D.wx = (ny + 3 > 13) ? ny + 3 : 13;
-    if (D.wx > nx) D.wx = nx;
-    D.col_len = ny > 43 ? ny : 43;
-    D.row_len = (ny + 8 > 48) ? ny + 8 : 48;
-    std::vector<float> S(ny), COL(D.col_len), ROW(D.row_len), W((size_t)D.wx * ny), WF(22 * 43);
-    eikf::Lane L{S.data(), COL.data(), ROW.data(), W.data(), WF.data()};
+    const eikf::Dims D = eikf::make_dims(nx, ny);
+    std::vector<float> SM(eikf::smem_floats_per_lane(D)), W((size_t)D.wx * ny), WF(22 * 43);
+    eikf::Lane L;
+    eikf::carve_shared(SM.data(), D, &L);
+    L.W = W.data(); L.WF = WF.data();
     eikf::LaneTask task;
     task.valid = true; task.iz = iz; task.slow = s; task.out = rows_out; task.out_rstride = nx; task.full = t;
     return eikf::solve_warp(D, L, task, rows, n_rows);
