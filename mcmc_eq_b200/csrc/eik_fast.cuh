@@ -257,6 +257,9 @@ EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inpl
 // end slots hold kStop, so a walk ends at the array ends by the very test that ends it at a local maximum of the
 // past column; S[-1] = S[ke] = INF stand for the cells the reference does not look at.
 constexpr float kStop = -1.0e30f;
+#ifdef EIKF_STATS
+static long g_stats[8];
+#endif
 
 EIK_HD void march_sweep(bool act, const float* P, float* C, const float* S, int ke, int* hint)
 {
@@ -342,7 +345,82 @@ EIK_HD void march_sweep(bool act, const float* P, float* C, const float* S, int 
     if (act) {
         const int first = (ans_b != 0x7fffffff) ? ans_b : ans_f;
         *hint = (first + 1 < rv_lo) ? first : -1;
+#ifdef EIKF_STATS
+        g_stats[0]++; if (*hint < 0) g_stats[1]++; if (nseg > 1) g_stats[2]++; if (nseg > 2) g_stats[3]++;
+        if (*hint < 0 && rv_lo <= 1) g_stats[4]++;
+#endif
     }
+}
+
+// ---- the march, two lock-step passes -----------------------------------------------------------------------
+// Without exact ties in the past column the order in which the reference visits the nodes of a line does not
+// matter, only who is timed from whom: a node whose past time is not below its upper neighbour's is timed from
+// that neighbour (the reference reaches it walking down from a local minimum), a node not below its lower
+// neighbour's from below, a local maximum from both (the smaller wins), and a node strictly below its upper
+// neighbour and not above its lower one is where the reference's search for a local minimum stops: a root, timed
+// by 1-D transmission.  So a column is two passes, one down the column and one up, every lane at the same depth
+// at the same time, with predicated stores instead of per-lane walks: straight-line code, no votes, no state
+// machine.  The passes also see an exact tie if there is one; such a column (4 in 100 000) is re-done by
+// march_sweep, which follows the reference's order literally.
+// P, C: indices -1 .. ke+1; P's end slots must hold kEdge (set by the caller); S[-1] = S[ke] = INF.
+constexpr float kEdge = 1.0e30f;
+
+EIK_HD bool march_sweep2(bool act, const float* P, float* C, const float* S, int ke)
+{
+    bool tie = false;
+    // ---- pass 1, k = 0 .. ke: roots and nodes timed from above (parent k-1)
+    {
+        float pprev = kEdge, pk = P[0], sprev = kInf, cn = kInf;
+#pragma unroll 4
+        for (int k = 0; k <= ke; k++) {
+            const float pnext = P[(long)(k + 1) * LS];
+            const float sk = S[(long)k * LS];
+            const float dt = pk - pprev;
+            const bool up = dt >= 0.f;                       // timed from node k-1
+            const bool root = !up && (pnext >= pk);          // the search for a local minimum stops here
+            tie = tie || (dt == 0.f);
+            const float lim = sprev * kRsqrt2;
+            const float s0sq = sprev * sprev;
+            float est = pk + sqrt_pos(fmaf(-dt, dt, s0sq));
+            float cv = (dt < lim) ? est : kInf;
+            const float dt2 = cn - pprev;
+            est = cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
+            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+            cv = fminf(cv, pk + sk);
+            cv = fminf(cv, fmaf(sprev, kSqrt2, pprev));
+            const float cmin = fminf(kInf, pk + eik::fmin_ref(sprev, sk));
+            const float val = up ? cv : (root ? cmin : kInf);
+            C[(long)k * LS] = val;
+            cn = val; pprev = pk; pk = pnext; sprev = sk;
+        }
+    }
+    // ---- pass 2, k = ke-1 .. 0: nodes timed from below (parent k+1); a local maximum keeps the smaller value
+    {
+        float pnx = P[(long)ke * LS], cn = C[(long)ke * LS];
+#pragma unroll 4
+        for (int k = ke - 1; k >= 0; k--) {
+            const float pk = P[(long)k * LS];
+            const float s0 = S[(long)k * LS];
+            const float hs1 = S[(long)(k - 1) * LS];
+            const float cold = C[(long)k * LS];
+            const float dt = pk - pnx;
+            const bool down = dt >= 0.f;
+            tie = tie || (dt == 0.f);
+            const float lim = s0 * kRsqrt2;
+            const float s0sq = s0 * s0;
+            float est = pk + sqrt_pos(fmaf(-dt, dt, s0sq));
+            float cv = fminf(cold, (dt < lim) ? est : kInf);
+            const float dt2 = cn - pnx;
+            est = cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
+            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+            cv = fminf(cv, pk + hs1);
+            cv = fminf(cv, fmaf(s0, kSqrt2, pnx));
+            const float val = down ? cv : cold;
+            if (down) C[(long)k * LS] = val;
+            cn = val; pnx = pk;
+        }
+    }
+    return act && tie;
 }
 
 // ---- perimeter <-> global window -------------------------------------------------------------------
@@ -411,14 +489,20 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
 #pragma unroll
             for (int r = 0; r < 8; r++) rr[r] = (out && r < n_rows) ? rows[r] : 0;
             if (b.active) {
-                col[-(long)LS] = kStop; col[(size_t)b.ny * LS] = kStop;
-                spare[-(long)LS] = kStop; spare[(size_t)b.ny * LS] = kStop;
+                col[-(long)LS] = kEdge; col[(size_t)b.ny * LS] = kEdge;
+                spare[-(long)LS] = kEdge; spare[(size_t)b.ny * LS] = kEdge;
             }
             while (EIKF_ANY(b.active && b.X1 < b.mx)) {
                 const bool need = b.active && b.X1 < b.mx;
                 int line = 0;
                 if (need) line = ++b.X1;
-                march_sweep(need, col, spare, L.S, b.my, &hint);
+                const bool tie = march_sweep2(need, col, spare, L.S, b.my);
+                if (EIKF_ANY(tie)) {   // an exact tie in the past column: follow the reference's order literally
+                    if (tie) { col[-(long)LS] = kStop; col[(size_t)b.ny * LS] = kStop; }
+                    int nohint = -1;
+                    march_sweep(tie, col, spare, L.S, b.my, &nohint);
+                    if (tie) { col[-(long)LS] = kEdge; col[(size_t)b.ny * LS] = kEdge; }
+                }
                 if (need) {
                     float* tmp = col; col = spare; spare = tmp;
                     if (out) {

@@ -29,3 +29,6 @@ extern "C" int emu_fast_time_2d(const float* s, int nx, int ny, int iz, float* t
     task.valid = true; task.iz = iz; task.slow = s; task.out = rows_out; task.out_rstride = nx; task.full = t;
     return eikf::solve_warp(D, L, task, rows, n_rows);
 }
+#ifdef EIKF_STATS
+extern "C" void emu_stats(long* out) { for (int i = 0; i < 8; i++) out[i] = eikf::g_stats[i]; }
+#endif
