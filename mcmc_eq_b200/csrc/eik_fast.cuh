@@ -452,6 +452,9 @@ EIK_HD int slow_line(float* t, const Box& b, const Medium& m, const Lane& L, int
                      int kb, int ke, bool refill)
 {
     eik::Grid<Medium> g = make_grid(t, b, m);
+#ifdef EIKF_STATS
+    g_stats[5]++; g_stats[6] += (ke - kb + 1); if (!refill) g_stats[7]++;
+#endif
     if (refill)
         for (int k = kb; k <= ke; k++) eik::node<AXIS>(g, line, k) = kInf;
     eik::sweep_line<AXIS>(g, line, future, kb, ke);
@@ -526,7 +529,9 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 bool slow = false, refill = true;
                 if (need) {
                     line = --b.Y0;
-                    if (b.preset_up || b.X1 >= b.mx) { slow = true; refill = false; }
+                    // the coarse grid's last column of cells is masked (INF): rows that reach it take the generic sweep;
+                    // the refined grid is not masked (src/time_2d.c:466), its rows are uniform up to the edge
+                    if (b.preset_up || (!FINE && b.X1 >= b.mx)) { slow = true; refill = false; }
                 }
                 const float c = need ? rowS(line) : 1.f;
                 const float c2 = (need && line - 1 >= 0) ? rowS(line - 1) : kInf;   // far < 0: no head wave
@@ -583,7 +588,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 bool slow = false;
                 if (need) {
                     line = ++b.Y1;
-                    if (b.X1 >= b.mx) slow = true;
+                    if (!FINE && b.X1 >= b.mx) slow = true;
                 }
                 const float c = need ? rowS(line - 1) : 1.f;
                 const float c2 = need ? rowS(line) : kInf;
