@@ -47,17 +47,50 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock, power and throttle reasons sampled through NVML every 10 ms while the timed region runs
+    (nvidia-smi -lms as the fallback when the NVML binding is missing)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.proc, self.rows = index, None, []
+        self.index, self.proc, self.rows, self.stop_flag, self.t, self.nvml = index, None, [], False, None, None
+
+    def _nvml_loop(self):
+        n, h = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
+            import pynvml as n
+            n.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            h = n.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.nvml = (n, h)
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -68,6 +101,15 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            if not self.rows:
+                return None
+            sm = sorted(r[0] for r in self.rows)
+            reasons = [k for k, b in self.BITS.items() if any(r[2] & b for r in self.rows)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "power_w_max": max(r[1] for r in self.rows),
+                    "samples": len(self.rows), "reasons": reasons, "source": "nvml, 10 ms"}
         if not self.proc:
             return None
         self.proc.terminate()
@@ -82,7 +124,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
-                "samples": len(rows), "reasons": reasons}
+                "samples": len(rows), "reasons": reasons, "source": "nvidia-smi -lms 50"}
 
 
 def dist_setup(n_gpus):

@@ -817,25 +817,30 @@ extern "C" int mq_snapshot(mq_handle* hh, int chain, int which, mq_record_fn fn,
         r.kind = MQ_REC_BEST;
         r.code = 'F';
     } else {
-        // current state: copy through the `best` path into a temporary snapshot is not needed -- read it directly
-        mq_models m;
-        memset(&m, 0, sizeof m);
-        const size_t md = h->md, ne = h->ne, ns = h->ns, n = h->n;
-        std::vector<int32_t> dim(n);
-        std::vector<float> z(n * md), vp(n * md), vpvs(n * md), eq(n * ne * 3), pres(n * ns), sres(n * ns), noise(n * 8), origin(n * ne);
-        m.n_chains = h->n; m.max_dim = h->md; m.n_events = h->ne; m.n_stations = h->ns;
-        m.dim = dim.data(); m.z = z.data(); m.vp = vp.data(); m.vpvs = vpvs.data(); m.eq = eq.data(); m.pres = pres.data();
-        m.sres = sres.data(); m.noise = noise.data(); m.origin = origin.data();
-        rc = mq_get_models(hh, &m);
-        if (rc != MQ_OK) return rc;
+        // current state of one chain, read straight from its current buffers
+        const size_t md = h->md, ne = h->ne, ns = h->ns, n = h->n, c = (size_t)chain;
+        cudaStream_t st = h->stream;
+        int32_t mcur = 0, ecur = 0, dim = 0;
         double rms = 0;
         int64_t acce = 0;
-        MQ_CUDA(cudaMemcpy(&rms, h->rms + chain, sizeof rms, cudaMemcpyDeviceToHost));
-        MQ_CUDA(cudaMemcpy(&acce, s->acce + chain, sizeof acce, cudaMemcpyDeviceToHost));
-        r.chain = chain; r.kind = MQ_REC_CURRENT; r.code = 'S'; r.number = acce > 0 ? acce - 1 : 0; r.dim = dim[chain]; r.rms = rms;
-        r.z = z.data() + chain * md; r.vp = vp.data() + chain * md; r.vpvs = vpvs.data() + chain * md;
-        r.eq = eq.data() + chain * ne * 3; r.origin = origin.data() + chain * ne; r.pres = pres.data() + chain * ns;
-        r.sres = sres.data() + chain * ns; r.noise = noise.data() + 8 * (size_t)chain;
+        MQ_CUDA(cudaMemcpyAsync(&mcur, h->mcur + c, sizeof mcur, cudaMemcpyDeviceToHost, st));
+        MQ_CUDA(cudaMemcpyAsync(&ecur, h->ecur + c, sizeof ecur, cudaMemcpyDeviceToHost, st));
+        MQ_CUDA(cudaMemcpyAsync(&rms, h->rms + c, sizeof rms, cudaMemcpyDeviceToHost, st));
+        MQ_CUDA(cudaMemcpyAsync(&acce, s->acce + c, sizeof acce, cudaMemcpyDeviceToHost, st));
+        MQ_CUDA(cudaStreamSynchronize(st));
+        buf.resize(3 * md + 4 * ne + 2 * ns + 8);
+        float* z = buf.data(); float* vp = z + md; float* vpvs = vp + md; float* eq = vpvs + md; float* origin = eq + 3 * ne;
+        float* pres = origin + ne; float* sres = pres + ns; float* noise = sres + ns;
+        const size_t mo = ((size_t)mcur * n + c) * md;
+#define D2H(dst, src, cnt) MQ_CUDA(cudaMemcpyAsync(dst, src, (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st))
+        D2H(&dim, h->dim + (size_t)mcur * n + c, 1);
+        D2H(z, h->z + mo, md); D2H(vp, h->vp + mo, md); D2H(vpvs, h->vpvs + mo, md);
+        D2H(eq, h->eq + c * ne * 3, 3 * ne); D2H(origin, h->origin + ((size_t)ecur * n + c) * ne, ne);
+        D2H(pres, h->pres + c * ns, ns); D2H(sres, h->sres + c * ns, ns); D2H(noise, h->noise + 8 * c, 8);
+#undef D2H
+        MQ_CUDA(cudaStreamSynchronize(st));
+        r.chain = chain; r.kind = MQ_REC_CURRENT; r.code = 'S'; r.number = acce > 0 ? acce - 1 : 0; r.dim = dim; r.rms = rms;
+        r.z = z; r.vp = vp; r.vpvs = vpvs; r.eq = eq; r.origin = origin; r.pres = pres; r.sres = sres; r.noise = noise;
         fn(user, &r);
         return MQ_OK;
     }

@@ -94,12 +94,19 @@ struct Box {
     int active;
 };
 
-// Correctly rounded sqrt for normal positive arguments: the rsqrt + Newton sequence the compiler emits for
-// sqrtf(), without its range check (arguments here are products of slownesses, far from denormal or huge; a
-// non-positive argument only occurs where the stencil is not selected and yields an ignored NaN).
+// Square root of a stencil radicand.  On the device this is the hardware approximation (one MUFU.SQRT, relative
+// error <= 2^-23, i.e. at most one ulp of a term that is itself <= one cell's slowness, ~0.5 s: < 6e-8 s) instead of
+// the correctly rounded rsqrt + Newton sequence (five instructions).  The sum t + sqrt() is rounded to an ulp of t,
+// which is 60 times coarser at t = 30 s, so the field moves by far less than the FP32-vs-reference difference the
+// parity tolerance max(1e-4 s, 2e-6 T) is stated for (tests/test_eikonal_gpu.py measures it).  A non-positive argument
+// only occurs where the stencil is not selected and yields an ignored NaN.  EIKF_EXACT_SQRT restores the Newton form.
 EIK_HD float sqrt_pos(float r)
 {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(EIKF_EXACT_SQRT)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r));
+    return y;
+#elif defined(__CUDA_ARCH__)
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r));
     const float s = r * y;
@@ -423,6 +430,89 @@ EIK_HD bool march_sweep2(bool act, const float* P, float* C, const float* S, int
     return act && tie;
 }
 
+// ---- the march, both passes in one loop -----------------------------------------------------------------------
+// The two passes of march_sweep2 never feed each other: a node timed from above cannot have a neighbour above it
+// that is timed from below unless the two past times are equal (a tie, handled elsewhere), and a root's value only
+// depends on the past column.  So the downward chain (A, k = i) and the upward chain (B, k = ke - i) run in the same
+// loop iteration as two independent dependency chains -- twice the instruction-level parallelism per warp, which is
+// what a kernel limited to ~2 warps per scheduler by its shared-memory footprint needs -- and meet in the middle;
+// whoever reaches a node second merges with fminf.  Same values as march_sweep2, bit for bit.
+EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int ke)
+{
+    bool tie = false;
+    // chain A state: node ka, parent ka-1;  chain B state: node kb, parent kb+1
+    float a_pprev = kEdge, a_pk = P[0], a_sprev = kInf, a_cn = kInf;
+    float b_pnx = kEdge, b_pk = P[(long)ke * LS], b_s0 = kInf, b_cn = kInf;
+    const float* pa = P + LS;                 // &P[ka + 1]
+    const float* sa = S;                      // &S[ka]
+    float* ca = C;                            // &C[ka]
+    const float* pb = P + (long)(ke - 1) * LS;   // &P[kb - 1]
+    const float* sb = S + (long)(ke - 1) * LS;   // &S[kb - 1]
+    float* cb = C + (long)ke * LS;            // &C[kb]
+
+    // one node of each chain; MERGE: the other chain has already been at these nodes
+    auto step = [&](auto merge) {
+        // ---- A: roots and nodes timed from above
+        float a_val;
+        {
+            const float pnext = *pa;
+            const float sk = *sa;
+            const float dt = a_pk - a_pprev;
+            const bool up = dt >= 0.f;
+            const bool root = !up && (pnext >= a_pk);
+            tie = tie || (dt == 0.f);
+            const float lim = a_sprev * kRsqrt2;
+            const float s0sq = a_sprev * a_sprev;
+            float est = a_pk + sqrt_pos(fmaf(-dt, dt, s0sq));
+            float cv = (dt < lim) ? est : kInf;
+            const float dt2 = a_cn - a_pprev;
+            est = a_cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
+            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+            cv = fminf(cv, a_pk + sk);
+            cv = fminf(cv, fmaf(a_sprev, kSqrt2, a_pprev));
+            const float cmin = fminf(kInf, a_pk + eik::fmin_ref(a_sprev, sk));
+            a_val = up ? cv : (root ? cmin : kInf);
+            a_cn = a_val; a_pprev = a_pk; a_pk = pnext; a_sprev = sk;
+        }
+        if (decltype(merge)::value) a_val = fminf(a_val, *ca);
+        *ca = a_val;
+        // ---- B: roots and nodes timed from below
+        float b_val;
+        {
+            const float pprev = *pb;
+            const float hs1 = *sb;
+            const float dt = b_pk - b_pnx;
+            const bool down = dt >= 0.f;
+            const bool root = (b_pk < pprev) && !down;
+            const float lim = b_s0 * kRsqrt2;
+            const float s0sq = b_s0 * b_s0;
+            float est = b_pk + sqrt_pos(fmaf(-dt, dt, s0sq));
+            float cv = (dt < lim) ? est : kInf;
+            const float dt2 = b_cn - b_pnx;
+            est = b_cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
+            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+            cv = fminf(cv, b_pk + hs1);
+            cv = fminf(cv, fmaf(b_s0, kSqrt2, b_pnx));
+            const float cmin = fminf(kInf, b_pk + eik::fmin_ref(hs1, b_s0));
+            b_val = down ? cv : (root ? cmin : kInf);
+            b_cn = b_val; b_pnx = b_pk; b_pk = pprev; b_s0 = hs1;
+        }
+        if (decltype(merge)::value) b_val = fminf(b_val, *cb);
+        *cb = b_val;
+        pa += LS; sa += LS; ca += LS; pb -= LS; sb -= LS; cb -= LS;
+    };
+    struct No { enum { value = 0 }; };
+    struct Yes { enum { value = 1 }; };
+
+    const int n1 = (ke + 1) >> 1;            // iterations with ka < kb: nobody has been at either node
+#pragma unroll 2
+    for (int i = 0; i < n1; i++) step(No());
+    if (!(ke & 1)) C[(long)(ke >> 1) * LS] = kInf;   // odd node count: both chains meet on the middle node
+#pragma unroll 2
+    for (int i = n1; i <= ke; i++) step(Yes());
+    return act && tie;
+}
+
 // ---- perimeter <-> global window -------------------------------------------------------------------
 template <class G>
 EIK_HD void load_perimeter(const G& g, const Lane& L, int row_len)
@@ -499,7 +589,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 const bool need = b.active && b.X1 < b.mx;
                 int line = 0;
                 if (need) line = ++b.X1;
-                const bool tie = march_sweep2(need, col, spare, L.S, b.my);
+                const bool tie = march_sweep3(need, col, spare, L.S, b.my);
                 if (EIKF_ANY(tie)) {   // an exact tie in the past column: follow the reference's order literally
                     if (tie) { col[-(long)LS] = kStop; col[(size_t)b.ny * LS] = kStop; }
                     int nohint = -1;

@@ -90,7 +90,7 @@ bool eik_fast_supported(int nxmod, int nz)
 }
 
 // One warp per block: a warp owns 32 solves and its slice of shared memory, nothing is shared between warps.
-__global__ void __launch_bounds__(32) eik_fast_kernel(EikBatch b, eikf::Dims D)
+__global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims D)
 {
     extern __shared__ float smem[];
     const int lane = threadIdx.x;

@@ -1,0 +1,187 @@
+/* mcmc_eq_main.c -- the reference's command line on top of the B200 library (plain C host code, C ABI only).
+ *
+ *     mcmc_eq <config_eqx.dat> <out> <picks> [-n chains] [-d device] [-s seed] [-q]
+ *
+ * The first three arguments are the reference's (src/mcmc_eq.c:332-338; it ignores anything after them).
+ * With one chain (the default) <out> is written exactly like the reference writes it: a "sta ST" record, a
+ * "mod X." record every deci-th accepted model, the "bat BF" record and nine "cnt" lines
+ * (src/mcmc_eq.c:763,1163,1196-1207; format of print_model_raw :234-248).  With -n N the N chains that the
+ * reference would run as N processes (run/srun_mcmc_eq.sh:13,35) run concurrently on one GPU and each writes
+ * its own file: <out> is a printf pattern with one integer conversion ("rjx-%03d.out"); without a conversion
+ * the chain number is inserted before the extension ("rjx.out" -> "rjx-001.out", the naming scriptsV2/dispe.sh:29
+ * globs for).  Chain numbers start at 1 like the SLURM array index.
+ *
+ * Seeds: config line 32 first value > 0 seeds chain k with value + k (chain 0 == the configured seed);
+ * otherwise /dev/urandom (src/mcmc_eq.c:250-265,393-394).  -s overrides.  The random streams are this
+ * library's counter-based generator, not libc rand(): chains are statistically, not bitwise, the reference's.
+ *
+ * Unlike the reference (which exit(0)s on every error) the exit status is non-zero on failure.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../../include/mcmceq_b200.h"
+#include "mq_io.h"
+
+typedef struct {
+    int n_chains;
+    FILE** out;
+    const mqio_picks* pk;
+    long* written;
+} sink_t;
+
+static const char* kind_tag(int kind) { return kind == MQ_REC_MODEL ? "mod" : kind == MQ_REC_BEST ? "bat" : "sta"; }
+
+static int write_record(void* user, const mq_record* r)
+{
+    sink_t* s = (sink_t*)user;
+    char code[3];
+    if (r->chain < 0 || r->chain >= s->n_chains) return 1;
+    if (r->kind == MQ_REC_MODEL) { code[0] = r->code; code[1] = '.'; }     /* "Q." "P." ... src/mcmc_eq.c:870-1096 */
+    else if (r->kind == MQ_REC_BEST) { code[0] = 'B'; code[1] = 'F'; }     /* :1196 */
+    else { code[0] = 'S'; code[1] = 'T'; }                                  /* :763  */
+    code[2] = 0;
+    mqio_write_record(s->out[r->chain], kind_tag(r->kind), code, (long)r->number, (long)r->dim, r->rms, r->noise, r->z,
+                      r->vp, r->vpvs, s->pk->view.n_events, r->eq, s->pk->reftime, r->origin, s->pk->view.n_stations,
+                      r->pres, r->sres);
+    s->written[r->chain]++;
+    return 0;
+}
+
+static unsigned long urandom_seed(void)
+{
+    unsigned long v = (unsigned long)time(NULL);
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (f) { if (fread(&v, sizeof v, 1, f) != 1) v = (unsigned long)time(NULL); fclose(f); }
+    return v;
+}
+
+static void out_name(char* dst, size_t cap, const char* pattern, int n_chains, int chain1)
+{
+    const char* pct = strchr(pattern, '%');
+    if (n_chains == 1 && !pct) { snprintf(dst, cap, "%s", pattern); return; }
+    if (pct) { snprintf(dst, cap, pattern, chain1); return; }
+    {
+        const char* dot = strrchr(pattern, '.');
+        const char* slash = strrchr(pattern, '/');
+        if (dot && (!slash || dot > slash)) snprintf(dst, cap, "%.*s-%03d%s", (int)(dot - pattern), pattern, chain1, dot);
+        else snprintf(dst, cap, "%s-%03d", pattern, chain1);
+    }
+}
+
+#define FAIL(...) do { fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); rc = 1; goto done; } while (0)
+#define MQ(call) do { int rc_ = (call); if (rc_ != MQ_OK) FAIL("%s failed (%d): %s", #call, rc_, mq_last_error()); } while (0)
+
+int main(int argc, char** argv)
+{
+    int rc = 0, n_chains = 1, device = 0, quiet = 0, i, c;
+    long seed_arg = -1;
+    mq_config cfg;
+    mqio_picks pk;
+    mq_handle* h = NULL;
+    sink_t sink;
+    int64_t* counts = NULL;
+    double *ll = NULL, *rms = NULL;
+    long iters_done = 0;
+    const char* env;
+    clock_t t0;
+
+    memset(&pk, 0, sizeof pk);
+    memset(&sink, 0, sizeof sink);
+    if (argc < 4) {
+        fprintf(stderr, "usage: %s config_eqx.dat outfile picks [-n chains] [-d device] [-s seed] [-q]\n", argv[0]);
+        return 2;
+    }
+    if ((env = getenv("MCMCEQ_CHAINS")) != NULL) n_chains = atoi(env);
+    if ((env = getenv("MCMCEQ_DEVICE")) != NULL) device = atoi(env);
+    for (i = 4; i < argc; i++) {
+        if (!strcmp(argv[i], "-n") && i + 1 < argc) n_chains = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-s") && i + 1 < argc) seed_arg = atol(argv[++i]);
+        else if (!strcmp(argv[i], "-q")) quiet = 1;
+        /* anything else is ignored, as the reference ignores extra arguments */
+    }
+    if (n_chains < 1) n_chains = 1;
+
+    if (mqio_read_config(argv[1], &cfg) != MQ_OK) FAIL("%s", mqio_last_error());
+    if (mqio_read_picks(argv[3], &pk) != MQ_OK) FAIL("%s", mqio_last_error());
+    if (mqio_check_picks(&cfg, &pk, quiet ? NULL : stderr) != MQ_OK) FAIL("%s", mqio_last_error());
+    if (cfg.tria != 0) FAIL("config line 29: only the Voronoi parameterisation (0) is implemented");
+    if (cfg.aflag == 3) FAIL("config line 34: start from model.dat (aflag 3) is not implemented");
+
+    {
+        unsigned long seed = seed_arg >= 0 ? (unsigned long)seed_arg : (cfg.true_random > 0 ? (unsigned long)cfg.true_random : urandom_seed());
+        if (!quiet) fprintf(stderr, "%d chain(s) on device %d, seed %lu, %d events, %d stations, %d picks\n", n_chains, device, seed,
+                            pk.view.n_events, pk.view.n_stations, pk.view.n_picks);
+        MQ(mq_create(&cfg, &pk.view, n_chains, device, (uint64_t)seed, &h));
+    }
+
+    sink.n_chains = n_chains;
+    sink.pk = &pk;
+    sink.out = (FILE**)calloc((size_t)n_chains, sizeof(FILE*));
+    sink.written = (long*)calloc((size_t)n_chains, sizeof(long));
+    counts = (int64_t*)calloc((size_t)n_chains * 20, sizeof(int64_t));
+    ll = (double*)calloc((size_t)n_chains, sizeof(double));
+    rms = (double*)calloc((size_t)n_chains, sizeof(double));
+    if (!sink.out || !sink.written || !counts || !ll || !rms) FAIL("out of memory");
+    for (c = 0; c < n_chains; c++) {
+        char name[4096];
+        out_name(name, sizeof name, argv[2], n_chains, c + 1);
+        sink.out[c] = fopen(name, "w");
+        if (!sink.out[c]) FAIL("Could not open: %s", name);
+    }
+
+    /* start models + first forward (src/mcmc_eq.c:559-765) */
+    t0 = clock();
+    MQ(mq_init_chains(h));
+    MQ(mq_get_stats(h, counts, ll, rms));
+    if (!quiet) {
+        const long ms = (long)((clock() - t0) * 1000 / CLOCKS_PER_SEC);
+        fprintf(stderr, "Time taken %ld seconds %ld milliseconds\n", ms / 1000, ms % 1000);
+        for (c = 0; c < n_chains && c < 10; c++)
+            fprintf(stderr, "Start model found with loglikelihood %f RMS=%f\n", ll[c], rms[c]);
+    }
+    for (c = 0; c < n_chains; c++) MQ(mq_snapshot(h, c, 0, write_record, &sink));
+
+    /* main loop (src/mcmc_eq.c:845-1192): the chain ends after j_max_start + j_max_main ACCEPTED models.  Each
+     * chain holds one pending decimated record, so the records are drained at least every `deci` iterations. */
+    {
+        const long target = (long)cfg.j_max_start + (long)cfg.j_max_main;
+        int chunk = cfg.deci > 0 ? cfg.deci : 1000;
+        if (chunk > 2000) chunk = 2000;
+        for (;;) {
+            int lost = 0, running = 0;
+            MQ(mq_step(h, chunk, NULL));
+            iters_done += chunk;
+            MQ(mq_drain(h, write_record, &sink, &lost));
+            if (lost) fprintf(stderr, "warning: %d decimated record(s) were overwritten before being written\n", lost);
+            MQ(mq_get_stats(h, counts, ll, rms));
+            for (c = 0; c < n_chains; c++)
+                if (counts[20 * c + 17] < target) running++;
+            if (!quiet) {
+                double a = 0, r = 0;
+                for (c = 0; c < n_chains; c++) { a += (double)counts[20 * c + 17]; r += (double)counts[20 * c + 18]; }
+                fprintf(stderr, "Test  %8ld  chains running %d/%d  RMS(chain 1)=%16.10f [s] %5.1f accepted\n", iters_done, running,
+                        n_chains, rms[0], 100.0 * a / (a + r > 0 ? a + r : 1));
+            }
+            if (!running) break;
+        }
+    }
+
+    /* best model and diagnostics (src/mcmc_eq.c:1196-1207) */
+    for (c = 0; c < n_chains; c++) {
+        MQ(mq_snapshot(h, c, 1, write_record, &sink));
+        mqio_write_counts(sink.out[c], counts + 20 * c);
+    }
+
+done:
+    if (sink.out)
+        for (c = 0; c < n_chains; c++)
+            if (sink.out[c]) fclose(sink.out[c]);
+    free(sink.out); free(sink.written); free(counts); free(ll); free(rms);
+    if (h) mq_destroy(h);
+    mqio_free_picks(&pk);
+    return rc;
+}
