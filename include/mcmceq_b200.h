@@ -147,6 +147,13 @@ int mq_forward(mq_handle* h, int calct, float* mf, float* origin);
 /* Same, for models passed in host memory: upload, forward, download -- the end-to-end call. */
 int mq_forward_host(mq_handle* h, const mq_models* m, int calct, float* mf, float* origin);
 
+/* For a host-driven loop built on mq_forward_host (the reference's own main): after mq_forward_host the device tables
+ * are those of the last call with calct != 0, exactly like the reference's tttpr/tttsr.  mq_tables_save /
+ * mq_tables_restore are the reference's backup and restore of them (the triple loops at src/mcmc_eq.c:856,1161 and
+ * :1171), as device-to-device copies.  Not needed with mq_step, which flips buffers instead. */
+int mq_tables_save(mq_handle* h);
+int mq_tables_restore(mq_handle* h);
+
 /* Full travel-time table of one chain in the reference layout ttt[nz][nz][nxmod]
  * (ttt[j][iz][i], src/misfit.c:281-288); phase 1 = P, 2 = S.  Recomputes that chain's table
  * with every receiver row kept; meant for parity tests and the setup_table_new shim. */
@@ -162,6 +169,30 @@ int mq_init_chains(mq_handle* h);
  * device RNG.  proposal_override: NULL = the config's balanced proposal strings
  * (src/mcmc_eq.c:769-834), else a string of proposal letters to draw from uniformly. */
 int mq_step(mq_handle* h, int n_iters, const char* proposal_override);
+
+/* ---- replay: one iteration driven by a recorded proposal stream instead of the device RNG -------------------
+ * The second correctness level of the path: the reference's own proposals (recorded from the unmodified reference,
+ * oracle/replay_log.c) are scored by this library and its accept/reject decisions compared with the reference's.
+ * For chain c: kind[c] is the arm of the proposal switch (src/mcmc_eq.c:866-1130; 0 = leave the chain alone),
+ * `proposed` holds the complete proposed state -- the arm decides what is read: dim/z/vp/vpvs for P V M B D, event
+ * q_idx[c] of eq for Q, pres/sres for R, noise for N --, log_fac[c] the proposal-ratio term (:1038,1070,1114),
+ * u[c] the uniform deviate of the accept test (:1141).  What mq_step does after drawing a proposal happens
+ * unchanged: table rebuild by calct, misfit, alpha12 = min(1, nexp(log_fac + new_ll - old_ll)), accept iff
+ * u < alpha12, buffer flips, counters, decimated records.  Outputs (any may be NULL): accepted[c], alpha[c],
+ * new_ll[c], mf[c*8 + 2*class+phase] = class sums of the proposal. */
+typedef struct mq_replay {
+    int32_t n_chains;
+    const char* kind;            /* [n_chains] */
+    const mq_models* proposed;
+    const int32_t* q_idx;        /* [n_chains] (read for 'Q' only; may be NULL when no chain proposes Q) */
+    const double* log_fac;       /* [n_chains] */
+    const float* u;              /* [n_chains] */
+    int32_t* accepted;
+    float* alpha;
+    double* new_ll;
+    float* mf;
+} mq_replay;
+int mq_replay_step(mq_handle* h, const mq_replay* r);
 
 /* Per-chain statistics (device -> host). counts[chain*20 + i]: 0 tested(nmod), then a/r pairs
  * for N,P,V,Q,R,M,B,D in the order of the reference's cnt lines (src/mcmc_eq.c:1199-1207),

@@ -71,6 +71,11 @@ class MqRecord(C.Structure):
                 ("pres", fp), ("sres", fp)]
 
 
+class MqReplay(C.Structure):
+    _fields_ = [("n_chains", C.c_int32), ("kind", C.c_char_p), ("proposed", C.POINTER(MqModels)), ("q_idx", ip),
+                ("log_fac", dp), ("u", fp), ("accepted", ip), ("alpha", fp), ("new_ll", dp), ("mf", fp)]
+
+
 RECORD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MqRecord))
 
 
@@ -93,10 +98,13 @@ def lib() -> C.CDLL:
         L.mq_get_models.argtypes = [C.c_void_p, C.POINTER(MqModels)]
         L.mq_forward.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.mq_forward_host.argtypes = [C.c_void_p, C.POINTER(MqModels), C.c_int, fp, fp]
+        L.mq_tables_save.argtypes = [C.c_void_p]
+        L.mq_tables_restore.argtypes = [C.c_void_p]
         L.mq_get_table.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
         L.mq_get_predictions.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.mq_init_chains.argtypes = [C.c_void_p]
         L.mq_step.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        L.mq_replay_step.argtypes = [C.c_void_p, C.POINTER(MqReplay)]
         L.mq_get_stats.argtypes = [C.c_void_p, lp, dp, dp]
         L.mq_drain.argtypes = [C.c_void_p, RECORD_FN, C.c_void_p, C.POINTER(C.c_int)]
         L.mq_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_int, RECORD_FN, C.c_void_p]
@@ -258,6 +266,12 @@ class Sampler:
         check(lib().mq_forward_host(self.h, C.byref(v), calct, _p(mf), _p(origin)))
         return mf, origin
 
+    def tables_save(self):
+        check(lib().mq_tables_save(self.h))
+
+    def tables_restore(self):
+        check(lib().mq_tables_restore(self.h))
+
     def table(self, chain: int, phase: int) -> np.ndarray:
         t = np.zeros((self.nz, self.nz, self.nxmod), np.float32)
         check(lib().mq_get_table(self.h, chain, phase, _p(t)))
@@ -274,6 +288,19 @@ class Sampler:
 
     def step(self, n_iters: int, override: str | None = None):
         check(lib().mq_step(self.h, n_iters, override.encode() if override else None))
+
+    def replay_step(self, kinds, proposed: "Models", q_idx, log_fac, u):
+        """One iteration driven by recorded proposals (mq_replay_step): kinds = one letter per chain ('\\0' skips)."""
+        n = self.n
+        kb = C.create_string_buffer(bytes(ord(k) if isinstance(k, str) else int(k) for k in kinds), n)
+        q = np.ascontiguousarray(q_idx, np.int32)
+        lf = np.ascontiguousarray(log_fac, np.float64)
+        uu = _f32(u)
+        acc, alpha, ll, mf = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float64), np.zeros((n, 8), np.float32)
+        v = proposed.view()
+        r = MqReplay(n, C.cast(kb, C.c_char_p), C.pointer(v), _p(q, ip), _p(lf, dp), _p(uu), _p(acc, ip), _p(alpha), _p(ll, dp), _p(mf))
+        check(lib().mq_replay_step(self.h, C.byref(r)))
+        return dict(accepted=acc, alpha=alpha, new_ll=ll, mf=mf)
 
     def sync(self):
         check(lib().mq_sync(self.h))

@@ -48,6 +48,7 @@ cudaError_t alloc_view(EvalView* v, int n)
     if ((e = dalloc(&v->r_idx, n))) return e;
     if ((e = dalloc(&v->r_d, 4 * (size_t)n))) return e;
     if ((e = dalloc(&v->ev_only, n))) return e;
+    v->pres_over = nullptr; v->sres_over = nullptr;
     return cudaSuccess;
 }
 void free_view(EvalView* v)
@@ -393,6 +394,23 @@ extern "C" int mq_forward_host(mq_handle* hh, const mq_models* m, int calct, flo
     if (rc != MQ_OK) return rc;
     return mq_forward(hh, calct, mf, origin);
 }
+
+// Host-driven use (a reference-style main that calls mq_forward_host per proposal): the device tables are those of
+// the last call with calct != 0.  The reference keeps a backup copy of its tables and restores it after a rejection
+// (src/mcmc_eq.c:856,1161,1171); these two calls are that backup / restore, device to device.
+static int tables_copy(mq_handle* hh, int from, int to, const char* who)
+{
+    if (!hh) { set_error("%s: null", who); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    if (!h->models_set) { set_error("%s: no models", who); return MQ_ERR_STATE; }
+    MQ_CUDA(cudaSetDevice(h->device));
+    const size_t half = (size_t)h->n * 2 * h->tab_stride;
+    MQ_CUDA(cudaMemcpyAsync(h->tab + (size_t)to * half, h->tab + (size_t)from * half, half * sizeof(float), cudaMemcpyDeviceToDevice,
+                            h->stream));
+    return MQ_OK;
+}
+extern "C" int mq_tables_save(mq_handle* hh) { return tables_copy(hh, 0, 1, "mq_tables_save"); }
+extern "C" int mq_tables_restore(mq_handle* hh) { return tables_copy(hh, 1, 0, "mq_tables_restore"); }
 
 extern "C" int mq_sync(mq_handle* hh)
 {

@@ -109,6 +109,12 @@ struct SamplerDev {
     Snapshot out, best;
     char *ps_start, *ps_main, *ps_over;
     int len_start, len_main, len_over;
+    // replay mode (mq_replay_step): injected uniform deviates and per-chain results of the last decision
+    float* u_inject;     // [n] or nullptr
+    float* r_alpha;      // [n]
+    int32_t* r_accept;   // [n]
+    double* r_newll;     // [n]
+    int32_t* r_qidx;     // [n] injected event index of a Q proposal
 };
 struct Sampler : SamplerDev {
     std::string over_host;
@@ -418,6 +424,55 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
     s.draws[c] = rng.draws;
 }
 
+// ---- replay: the proposal comes from a recorded stream instead of the RNG ------------------------------
+// Fills exactly what propose_kernel fills, from injected data: s.kind[c] the arm, the proposed model in the work
+// arrays s.wz/wvp/wvs (+ dim_in), the proposed event in v.q_xyz (+ s.r_qidx), the proposed station corrections in
+// v.pres_over/sres_over, the proposed sigmas in s.noise_new, the proposal ratio in s.log_fac.  No validity test and no
+// eligibility test: the recorded proposals passed the reference's own (src/mcmc_eq.c:945-951,1021,1059).
+__global__ void replay_setup_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView v, const int32_t* dim_in)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n) return;
+    const int n = p.n;
+    const int d_in = dim_in[c];   // may alias s.rebuilt: read before that is reset
+    v.q_idx[c] = -1; v.r_idx[c] = -1; v.ev_only[c] = -2;
+    const int mc = hd.mcur[c], ec = hd.ecur[c];
+    v.mbuf[c] = mc; v.tbuf[2 * c] = hd.tcur[2 * c]; v.tbuf[2 * c + 1] = hd.tcur[2 * c + 1]; v.ebuf[c] = ec;
+    s.not_valid[c] = 0; s.rebuilt[c] = 0;
+    const char kind = (char)s.kind[c];
+    if (kind == 0) return;
+    int calct = 0;
+    switch (kind) {
+    case 'Q': v.q_idx[c] = s.r_qidx[c]; v.ev_only[c] = s.r_qidx[c]; break;      // v.q_xyz was uploaded
+    case 'R': v.r_idx[c] = -2; v.ev_only[c] = -1; v.ebuf[c] = 1 - ec; break;
+    case 'N': v.ev_only[c] = -2; break;
+    case 'V': calct = 2; break;
+    case 'P': case 'M': case 'B': case 'D': calct = 3; break;
+    default: s.not_valid[c] = 1; break;
+    }
+    if (calct) {
+        const int mo = 1 - mc, d = d_in;
+        float* nz_ = hd.z + ((size_t)mo * n + c) * p.md;
+        float* nvp = hd.vp + ((size_t)mo * n + c) * p.md;
+        float* nvpvs = hd.vpvs + ((size_t)mo * n + c) * p.md;
+        for (int i = 0; i < d; i++) { nz_[i] = s.wz[(size_t)c * p.md + i]; nvp[i] = s.wvp[(size_t)c * p.md + i]; nvpvs[i] = s.wvs[(size_t)c * p.md + i]; }
+        hd.dim[mo * n + c] = d;
+        v.mbuf[c] = mo; v.ev_only[c] = -1; v.ebuf[c] = 1 - ec;
+        s.rebuilt[c] = calct;
+        if (p.cfg.eikonal == 1 && p.cfg.aflag != 1) {
+            for (int ph = 0; ph < 2; ph++) {
+                if (!(calct & (1 << ph))) continue;
+                const int tb = 1 - hd.tcur[2 * c + ph];
+                v.tbuf[2 * c + ph] = tb;
+                const int item = atomicAdd(hd.n_items, 1);
+                hd.item_chain[item] = c; hd.item_phase[item] = ph;
+                hd.item_tab[item] = hd.tab + (((size_t)tb * n + c) * 2 + ph) * p.tab_stride;
+            }
+        }
+    }
+    if (p.cfg.aflag == 1) v.ev_only[c] = -2;
+}
+
 // ---- accept / reject (src/mcmc_eq.c:1135-1191) -------------------------------------------------
 __global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView v)
 {
@@ -448,9 +503,14 @@ __global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView
     if (g.aflag == 1) alpha = 1.f;
     if (not_valid && g.aflag == 0) alpha = 0.f;
 
-    Philox rng(p.seed, (uint32_t)c, s.draws[c]);
-    const float u = rng.uniform();
-    s.draws[c] = rng.draws;
+    float u;
+    if (s.u_inject) u = s.u_inject[c];   // replay: the reference's own deviate, no draw is consumed
+    else {
+        Philox rng(p.seed, (uint32_t)c, s.draws[c]);
+        u = rng.uniform();
+        s.draws[c] = rng.draws;
+    }
+    if (s.r_alpha) { s.r_alpha[c] = alpha; s.r_accept[c] = (u < alpha) ? 1 : 0; s.r_newll[c] = new_ll; }
 
     if (u < alpha) {
         const int64_t number = s.acce[c];
@@ -474,12 +534,14 @@ __global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView
             float* pres = hd.pres + (size_t)c * p.ns;
             float* sres = hd.sres + (size_t)c * p.ns;
             const float nsm1 = (float)(p.ns - 1);
-            if (g.scor_flag <= 0)
+            if (idx == -2) {   // replay: the proposed corrections were given in full
+                for (int k = 0; k < p.ns; k++) { pres[k] = v.pres_over[(size_t)c * p.ns + k]; sres[k] = v.sres_over[(size_t)c * p.ns + k]; }
+            } else if (g.scor_flag <= 0)
                 for (int k = 0; k < p.ns; k++) {
                     pres[k] = (k == idx) ? __fadd_rn(pres[k], dx) : __fsub_rn(pres[k], __fdiv_rn(dx, nsm1));
                     sres[k] = (k == idx) ? __fadd_rn(sres[k], dy) : __fsub_rn(sres[k], __fdiv_rn(dy, nsm1));
                 }
-            if (g.scor_flag != 0) { pres[idx] = __fadd_rn(pres[idx], dx2); sres[idx] = __fadd_rn(sres[idx], dy2); }
+            if (idx != -2 && g.scor_flag != 0) { pres[idx] = __fadd_rn(pres[idx], dx2); sres[idx] = __fadd_rn(sres[idx], dy2); }
             if (g.aflag != 1) hd.ecur[c] = v.ebuf[c];
         } else if (kind == 'N') {
             for (int k = 0; k < 8; k++) hd.noise[8 * (size_t)c + k] = noise[k];
@@ -619,6 +681,7 @@ static int sampler_get(Handle* h, Sampler** out)
     TRY(dz(&s->log_fac, n)); TRY(dz(&s->noise_new, n * 8)); TRY(dz(&s->best_rms, n));
     TRY(dz(&s->wz, n * h->md)); TRY(dz(&s->wvp, n * h->md)); TRY(dz(&s->wvs, n * h->md));
     TRY(alloc_snapshot(&s->out, h)); TRY(alloc_snapshot(&s->best, h));
+    TRY(dz(&s->r_alpha, n)); TRY(dz(&s->r_accept, n)); TRY(dz(&s->r_newll, n)); TRY(dz(&s->r_qidx, n));
     const std::string a = balance(h->cfg.dstring_start, h->ne, h->ns, 10), b = balance(h->cfg.dstring_main, h->ne, h->ns, 20);
     s->len_start = (int)a.size(); s->len_main = (int)b.size();
     TRY(upload_string(&s->ps_start, a)); TRY(upload_string(&s->ps_main, b));
@@ -641,6 +704,9 @@ void sampler_destroy(Handle* h)
     cudaFree(s->best_rms); cudaFree(s->wz); cudaFree(s->wvp); cudaFree(s->wvs);
     free_snapshot(&s->out); free_snapshot(&s->best);
     cudaFree(s->ps_start); cudaFree(s->ps_main); cudaFree(s->ps_over);
+    cudaFree(s->u_inject); cudaFree(s->r_alpha); cudaFree(s->r_accept); cudaFree(s->r_newll); cudaFree(s->r_qidx);
+    cudaFree(h->prop_view.pres_over); cudaFree(h->prop_view.sres_over);
+    h->prop_view.pres_over = nullptr; h->prop_view.sres_over = nullptr;
     delete s;
     h->sampler = nullptr;
 }
@@ -723,13 +789,98 @@ extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override
             MQ_CUDA(launch_misfit(h, h->prop_view));
             MQ_CUDA(launch_totals(h, h->prop_view));
         }
-        accept_kernel<<<grid, 64, 0, st>>>(p, *h, s->dev(), h->prop_view);
+        SamplerDev free_running = s->dev();
+        free_running.u_inject = nullptr;     // the accept test draws from the chain's own stream
+        accept_kernel<<<grid, 64, 0, st>>>(p, *h, free_running, h->prop_view);
         count_launch();
         MQ_CUDA(cudaGetLastError());
         snapshot_kernel<<<h->n, 128, 0, st>>>(p, *h, s->dev());
         count_launch();
         MQ_CUDA(cudaGetLastError());
     }
+    return MQ_OK;
+}
+
+// Replay of a recorded proposal stream: see include/mcmceq_b200.h.
+extern "C" int mq_replay_step(mq_handle* hh, const mq_replay* r)
+{
+    if (!hh || !r || !r->kind || !r->proposed || !r->u || !r->log_fac) { set_error("mq_replay_step: null"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    const mq_models* m = r->proposed;
+    if (r->n_chains != h->n || m->n_chains != h->n || m->n_events != h->ne || m->n_stations != h->ns || m->max_dim < 1) {
+        set_error("mq_replay_step: shape mismatch"); return MQ_ERR_ARG;
+    }
+    if (!h->models_set) { set_error("mq_replay_step: no models (mq_set_models or mq_init_chains first)"); return MQ_ERR_STATE; }
+    MQ_CUDA(cudaSetDevice(h->device));
+    Sampler* s;
+    int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    if (!s->started || !h->forward_done) {
+        rc = start_sampler_state(h, s);
+        if (rc != MQ_OK) return rc;
+    }
+    const size_t n = h->n, md = h->md, ne = h->ne, ns = h->ns;
+    cudaStream_t st = h->stream;
+    if (!s->u_inject) MQ_CUDA(dz(&s->u_inject, n));
+    if (!h->prop_view.pres_over) { MQ_CUDA(dz(&h->prop_view.pres_over, n * ns)); MQ_CUDA(dz(&h->prop_view.sres_over, n * ns)); }
+    // stage the injected proposal
+    std::vector<int32_t> kind(n), dim(n), qidx(n, 0);
+    std::vector<float> wz(n * md, 0.f), wvp(n * md, 1.f), wvs(n * md, 1.f), qxyz(3 * n, 0.f);
+    for (size_t c = 0; c < n; c++) {
+        kind[c] = (unsigned char)r->kind[c];
+        if (kind[c] && !strchr("QRPVMBDN", kind[c])) { set_error("mq_replay_step: unknown proposal letter '%c'", kind[c]); return MQ_ERR_ARG; }
+        dim[c] = m->dim[c];
+        if (dim[c] < 1 || dim[c] > (int)md || dim[c] > m->max_dim) { set_error("mq_replay_step: chain %zu: %d nuclei", c, dim[c]); return MQ_ERR_ARG; }
+        for (int i = 0; i < dim[c]; i++) {
+            wz[c * md + i] = m->z[c * m->max_dim + i]; wvp[c * md + i] = m->vp[c * m->max_dim + i]; wvs[c * md + i] = m->vpvs[c * m->max_dim + i];
+        }
+        if (kind[c] == 'Q') {
+            const int q = r->q_idx ? r->q_idx[c] : -1;
+            if (q < 0 || q >= (int)ne) { set_error("mq_replay_step: chain %zu: event index %d", c, q); return MQ_ERR_ARG; }
+            qidx[c] = q;
+            for (int k = 0; k < 3; k++) qxyz[3 * c + k] = m->eq[(c * ne + q) * 3 + k];
+        }
+    }
+    MQ_CUDA(cudaMemcpyAsync(s->kind, kind.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(s->r_qidx, qidx.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(s->rebuilt, dim.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));   // staging for dim_in
+    MQ_CUDA(cudaMemcpyAsync(s->wz, wz.data(), n * md * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(s->wvp, wvp.data(), n * md * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(s->wvs, wvs.data(), n * md * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(h->prop_view.q_xyz, qxyz.data(), 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(h->prop_view.pres_over, m->pres, n * ns * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(h->prop_view.sres_over, m->sres, n * ns * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(s->noise_new, m->noise, n * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(s->log_fac, r->log_fac, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaMemcpyAsync(s->u_inject, r->u, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    MQ_CUDA(cudaStreamSynchronize(st));   // the staging vectors go out of scope below
+
+    const SamplerParams p = make_params(h);
+    const int grid = (h->n + 63) / 64;
+    MQ_CUDA(cudaMemsetAsync(h->n_items, 0, sizeof(int32_t), st));
+    // dim_in lives in s->rebuilt until the setup kernel overwrites it per chain (read before written by the same thread)
+    replay_setup_kernel<<<grid, 64, 0, st>>>(p, *h, s->dev(), h->prop_view, s->rebuilt);
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    if (h->cfg.aflag != 1) {
+        if (h->cfg.eikonal == 1) {
+            MQ_CUDA(launch_rasterise(h, h->prop_view, 2 * h->n));
+            MQ_CUDA(launch_tables(h, 2 * h->n));
+        }
+        MQ_CUDA(launch_misfit(h, h->prop_view));
+        MQ_CUDA(launch_totals(h, h->prop_view));
+    }
+    accept_kernel<<<grid, 64, 0, st>>>(p, *h, s->dev(), h->prop_view);
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    snapshot_kernel<<<h->n, 128, 0, st>>>(p, *h, s->dev());
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    if (r->accepted) MQ_CUDA(cudaMemcpyAsync(r->accepted, s->r_accept, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (r->alpha) MQ_CUDA(cudaMemcpyAsync(r->alpha, s->r_alpha, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (r->new_ll) MQ_CUDA(cudaMemcpyAsync(r->new_ll, s->r_newll, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (r->mf) MQ_CUDA(cudaMemcpyAsync(r->mf, h->mf_eval, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MQ_CUDA(cudaStreamSynchronize(st));
     return MQ_OK;
 }
 

@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(128) misfit_kernel(MisfitParams p)
     const int ridx = p.v.r_idx[c];
     const float* rd = p.v.r_d + 4 * (size_t)c;
     const float nsm1 = (float)(p.ns - 1);
-    const float* pres = p.pres + (size_t)c * p.ns;
-    const float* sres = p.sres + (size_t)c * p.ns;
+    const float* pres = (ridx == -2) ? p.v.pres_over + (size_t)c * p.ns : p.pres + (size_t)c * p.ns;
+    const float* sres = (ridx == -2) ? p.v.sres_over + (size_t)c * p.ns : p.sres + (size_t)c * p.ns;
 
     const int b = p.pk.ev_off[e], end = p.pk.ev_off[e + 1], npk = p.pk.n_p[e];
     const float* tabP = p.tab + (((size_t)p.v.tbuf[2 * c] * p.n + c) * 2 + 0) * p.tab_stride;

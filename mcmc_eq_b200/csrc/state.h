@@ -40,9 +40,11 @@ struct EvalView {
     int32_t* ebuf;     // [n]   evsum/origin buffer to write
     int32_t* q_idx;    // [n]   event whose hypocentre is overridden by q_xyz (-1: none)
     float* q_xyz;      // [n][3]
-    int32_t* r_idx;    // [n]   station whose correction is perturbed (-1: none)
+    int32_t* r_idx;    // [n]   station whose correction is perturbed (-1: none; -2: take pres_over/sres_over instead)
     float* r_d;        // [n][2] dP, dS of the perturbation
     int32_t* ev_only;  // [n]   >= 0: evaluate only this event (result in evq/oq); -1: all; -2: none
+    float* pres_over;  // [n][ns] proposed station corrections given in full (replay mode, mq_replay_step) or nullptr
+    float* sres_over;
 };
 
 struct Handle {

@@ -117,3 +117,29 @@ def test_straight_ray_branch(oracle):
         _check_sums(mf[c], rmf, 5e-6)
         assert np.abs(origin[c] - rorg).max() < 2e-5
     smp.close()
+
+
+def test_host_driven_loop_with_table_backup(oracle):
+    """The function seam used the way the reference's main uses cal_fit_newx: tables are those of
+    the last call with calct != 0; mq_tables_save / mq_tables_restore stand for the reference's backup and restore of them
+    (src/mcmc_eq.c:856,1161,1171).  Sequence: model A (calct 3) -> save -> model B (calct 3, "rejected") -> restore ->
+    hypocentre change on A (calct 0) must score against A's tables."""
+    import mcmc_eq_b200 as mq
+    rng = np.random.default_rng(21)
+    d = tempfile.mkdtemp(prefix="mqf_")
+    cfgp, pkp = inputs.materialise("example2", d)
+    cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
+    smp = mq.Sampler(cfg, pk, 1, 0, 1)
+    a, b = fh.random_states(rng, cfg, pk, 2)
+    mfa, _ = smp.forward_host(fh.fill_models(smp.new_models(32), [a]), 3)
+    smp.tables_save()
+    smp.forward_host(fh.fill_models(smp.new_models(32), [b]), 3)
+    smp.tables_restore()
+    a2 = dict(a)
+    a2["eq"] = a["eq"].copy()
+    a2["eq"][5] += np.float32([0.7, -0.4, 1.1])
+    mf2, org2 = smp.forward_host(fh.fill_models(smp.new_models(32), [a2]), 0)
+    ref, rorg, *_ = fh.oracle_forward(cfg, pk, a2["z"], a2["vp"], a2["vpvs"], a2["eq"], a2["pres"], a2["sres"])
+    assert np.allclose(mf2[0], ref, rtol=2e-5) and np.allclose(org2[0], rorg, atol=2e-5)
+    assert not np.allclose(mf2[0], mfa[0], rtol=1e-6)
+    smp.close()

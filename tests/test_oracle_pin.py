@@ -127,3 +127,32 @@ def test_chain_scalars_match_reference_live(oracle, reflib):
         assert a == b
         n_valid += (a == 0)
     assert 20 < n_valid < 280
+
+
+def test_chain_oracle_reproduces_every_recorded_decision(oracle):
+    """Chain level of the oracle: the reference's proposal stream (tests/golden/replay_example2.npz, recorded from the
+    unmodified reference by oracle/replay_log.c) scored with the oracle's restatement -- class sums from fm_misfit +
+    tables for a sample of the proposals, likelihood / proposal ratio / alpha from oracle/chain.c for all of them --
+    must give the reference's accept/reject decision for all 312 evaluated proposals."""
+    import tempfile
+    import mcmc_eq_b200 as mq
+    from tests import replay, fwd_helpers as fh
+    log = replay.load("example2")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=77)
+        cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
+    assert len(log["u"]) == 313 and int(log["accepted"][1:].sum()) == 200
+    old_ll = replay.loglik(log["mf"][0], log["noise"][0])
+    kinds = {}
+    for i, kind, q, lf, u, acc, cur, prop in replay.proposals(log, cfg, pk.n_class):
+        kinds[kind] = kinds.get(kind, 0) + 1
+        new_ll = replay.loglik(log["mf"][i], prop["noise"])
+        alpha = oracle.ch_alpha(lf, new_ll, old_ll)
+        assert (u < alpha) == acc, (i, kind, u, alpha, acc)
+        if acc:
+            old_ll = new_ll
+        if i % 40 == 1 or kind in "BD":   # full forward of the oracle on a sample (each costs ~2 x 61 eikonal solves)
+            mf, origin, _r, _t = fh.oracle_forward(cfg, pk, prop["z"], prop["vp"], prop["vpvs"], prop["eq"], prop["pres"], prop["sres"])
+            assert np.array_equal(mf, log["mf"][i]), (i, kind)
+            assert np.array_equal(origin, prop["origin"])
+    assert set(kinds) == set("QRPVMBDN"), kinds     # every arm of the proposal switch occurs in the recorded chain

@@ -1,0 +1,78 @@
+"""Chain-level parity (SURVEY.md section 8c level 3): the reference's own proposal stream -- every proposed model of a
+recorded chain of the UNMODIFIED reference (tests/golden/replay_example2.npz, oracle/replay_log.c), the uniform deviate
+of each accept test and the proposal-ratio term of its arm -- is replayed through mq_replay_step; the library must take
+the reference's accept/reject decision every time, except at declared near-ties.
+
+Near-tie rule.  The decision is u < alpha12 = min(1, exp(log_fac + new_ll - old_ll)), i.e. log u < log_fac + dll.  The
+class sums of this library agree with the reference's to 1e-5 relative (FP32 eikonal restated, |dT| <= 1e-4 s), so a
+log-likelihood of magnitude |ll| carries an uncertainty of about 1e-5 |ll|; a proposal whose margin
+|log u - (log_fac + dll_ref)| is below  2e-5 * max(|new_ll_ref|, |old_ll_ref|) + 1e-3  is decided by less than that and is
+excluded (counted and reported).  After an excluded mismatch the chain is put back on the reference's state."""
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import inputs, replay
+
+pytestmark = pytest.mark.gpu
+
+
+def _models_from(smp, st, n):
+    m = smp.new_models(64)
+    for c in range(n):
+        d = st["dim"]
+        m.dim[c] = d
+        m.z[c, :d], m.vp[c, :d], m.vpvs[c, :d] = st["z"], st["vp"], st["vpvs"]
+        m.eq[c], m.pres[c], m.sres[c], m.noise[c] = st["eq"], st["pres"], st["sres"], st["noise"]
+    return m
+
+
+def test_replayed_reference_chain_makes_the_reference_decisions():
+    import mcmc_eq_b200 as mq
+    log = replay.load("example2")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=77)
+        cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
+    n = 3                                                     # three copies of the chain: results must be identical
+    smp = mq.Sampler(cfg, pk, n, 0, 1)
+    smp.set_models(_models_from(smp, replay.state_of(log, 0), n))
+    mf0, _ = smp.forward(3)
+    assert np.allclose(mf0[0], log["mf"][0], rtol=2e-5)
+    old_ll_ref = replay.loglik(log["mf"][0], log["noise"][0])
+    n_eval = n_match = n_tie = 0
+    worst_ll = 0.0
+    kinds_seen = set()
+    for i, kind, q, lf, u, acc, cur, prop in replay.proposals(log, cfg, pk.n_class):
+        out = smp.replay_step([kind] * n, _models_from(smp, prop, n), [max(q, 0)] * n, [lf] * n, [u] * n)
+        assert (out["accepted"] == out["accepted"][0]).all() and (out["new_ll"] == out["new_ll"][0]).all()
+        new_ll_ref = replay.loglik(log["mf"][i], prop["noise"])
+        n_eval += 1
+        kinds_seen.add(kind)
+        # class sums of the proposal vs the reference's own (1e-5 relative, stated in SURVEY.md section 8c level 2)
+        assert np.allclose(out["mf"][0], log["mf"][i], rtol=2e-5, atol=1e-6), (i, kind)
+        worst_ll = max(worst_ll, abs(out["new_ll"][0] - new_ll_ref) / max(abs(new_ll_ref), 1.0))
+        if bool(out["accepted"][0]) == acc:
+            n_match += 1
+        else:
+            margin = abs(np.log(max(u, 1e-30)) - (lf + new_ll_ref - old_ll_ref))
+            assert margin <= 2e-5 * max(abs(new_ll_ref), abs(old_ll_ref)) + 1e-3, (i, kind, u, out["alpha"][0], margin)
+            n_tie += 1
+            st = prop if acc else cur                          # back onto the reference's trajectory
+            smp.set_models(_models_from(smp, st, n))
+            smp.forward(3)
+        if acc:
+            old_ll_ref = new_ll_ref
+    assert n_eval == 312 and kinds_seen == set("QRPVMBDN")
+    assert n_match + n_tie == n_eval and n_tie <= 6, (n_match, n_tie)
+    assert worst_ll < 2e-5
+    # the replayed chain ends in the reference's final state with the reference's bookkeeping
+    counts, ll, rms = smp.stats()
+    m = smp.get_models(64)
+    last = replay.state_of(log, int(np.nonzero(log["accepted"])[0][-1]))
+    assert m.dim[0] == last["dim"] and np.array_equal(m.z[0, :last["dim"]], last["z"]) and np.array_equal(m.eq[0], last["eq"])
+    assert np.array_equal(m.pres[0], last["pres"]) and np.array_equal(m.noise[0], last["noise"])
+    if n_tie == 0:
+        assert counts[0, 17] == 200 and counts[0, 18] == 112 and counts[0, 0] == 312
+    print(f"replay: {n_match}/{n_eval} decisions identical, {n_tie} declared near-ties, worst |dll|/|ll| = {worst_ll:.2e}")
+    smp.close()

@@ -5,6 +5,9 @@
   eikonal_ref.npz              : time_2d fields of the compiled reference (oracle/_ref) for seeded models
   forward_ref.npz              : cal_fit_newx class sums / origin times of the compiled reference
   chain_ref_example2.out       : a short fixed-seed chain of the reference mcmc_eq binary
+  replay_example2.npz          : the proposal stream of that same chain (every proposed model, the uniform deviate of
+                                 its accept test, the reference's class sums and decision), recorded from the unmodified
+                                 reference by symbol interposition (oracle/replay_log.c)
 
 Usage: python tools/make_golden.py   (needs /root/reference and oracle/_ref built: make -C oracle)
 """
@@ -141,6 +144,49 @@ def chain_ref():
     print("chain_ref:", txt.count("\n"), "lines")
 
 
+def read_replay_log(path):
+    """oracle/replay_log.c's binary log -> dict of padded arrays."""
+    b = open(path, "rb").read()
+    magic, noq, nos = np.frombuffer(b, np.int32, 3, 0)
+    assert magic == 0x4d435251
+    off = 12
+    recs = []
+    while off < len(b):
+        calct, dim, acc = np.frombuffer(b, np.int32, 3, off); off += 12
+        f = lambda n: np.frombuffer(b, np.float32, n, off).copy()
+        r = dict(calct=calct, dim=dim, accepted=acc)
+        for name, n in (("u", 1), ("mf", 8), ("noise", 8), ("z", dim), ("vp", dim), ("vpvs", dim), ("eq", 3 * noq), ("pres", nos),
+                        ("sres", nos), ("origin", noq)):
+            r[name] = f(n); off += 4 * n
+        recs.append(r)
+    n, md = len(recs), max(r["dim"] for r in recs)
+    out = dict(calct=np.array([r["calct"] for r in recs], np.int32), dim=np.array([r["dim"] for r in recs], np.int32),
+               accepted=np.array([r["accepted"] for r in recs], np.int32), u=np.array([r["u"][0] for r in recs], np.float32))
+    for name in ("mf", "noise", "eq", "pres", "sres", "origin"):
+        out[name] = np.stack([r[name] for r in recs])
+    out["eq"] = out["eq"].reshape(n, noq, 3)
+    for name in ("z", "vp", "vpvs"):
+        a = np.zeros((n, md), np.float32)
+        for i, r in enumerate(recs):
+            a[i, :r["dim"]] = r[name]
+        out[name] = a
+    return out
+
+
+def replay_ref():
+    """Proposal stream of the chain_ref chain (same config and seed), from the unmodified reference."""
+    exe = os.path.join(util.REF_DIR, "replay_log")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=77)
+        outp, logp = os.path.join(d, "rjx-000.out"), os.path.join(d, "log.bin")
+        subprocess.run([exe, logp, cfgp, outp, pkp], check=True, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        # the interposed run must be the reference's own chain, byte for byte
+        assert open(outp).read() == open(os.path.join(G, "chain_ref_example2.out")).read()
+        log = read_replay_log(logp)
+    np.savez_compressed(os.path.join(G, "replay_example2.npz"), **log)
+    print("replay_ref:", len(log["u"]), "records,", int(log["accepted"][1:].sum()), "accepted")
+
+
 if __name__ == "__main__":
     os.makedirs(G, exist_ok=True)
     inputs_of("example", os.path.join(REF, "Example/config_eqx.dat"), os.path.join(REF, "Example/picks_synth"))
@@ -148,4 +194,5 @@ if __name__ == "__main__":
     eikonal_fields()
     forward_ref()
     chain_ref()
+    replay_ref()
     print(subprocess.run(["du", "-sh", G], capture_output=True, text=True).stdout)
