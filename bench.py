@@ -39,6 +39,18 @@ UNIT = "proposals/s"
 SMEM_PEAK_GBS = 148 * 128 * 1.965   # 148 SM x 128 B/clk x 1.965 GHz = 37.2 TB/s
 
 
+def kernel_traffic(kernel, solves_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same workload), scaled to this run's launch size."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(kernel)
+    if not t:
+        return None
+    return float(t["dram_bytes_per_launch"]) * solves_per_launch / float(t["solves_per_launch"])
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -208,21 +220,25 @@ def cpu_baseline(cfg, pk, truth, budget_s, steps=1, warmup=0):
     try:
         write_picks(pk, os.path.join(d, "picks"), truth["t64"])
         cd = config_to_dict(cfg)
-        # calibrate: a very short batch tells how many proposals one accepted model costs and how fast they are
-        p0, w0 = run_reference_batch(d, exe, cd, cores, 3, 1000)
-        rate = max(p0 / max(w0, 1e-3), 1e-3)                       # proposals/s, all cores
-        per_acc = max(p0 / (3.0 * cores), 1.0)
+        # The reference's loop counter is ACCEPTED models (src/mcmc_eq.c:845), so the run time of a long chain is not
+        # bounded by its configuration.  Bounded sample: short fresh chains (15 accepted models each, one process per
+        # core), batch after batch until the time budget of a step is used; proposals = sum of the cnt lines.
+        accepted = 15
         per_step = budget_s / max(steps + warmup, 1)
-        accepted = int(max(3, min(400, (rate / cores) * per_step * 0.8 / per_acc)))
-        tot_p, tot_w = 0, 0.0
+        tot_p, tot_w, batches = 0, 0.0, 0
         for s in range(warmup + steps):
-            p, w = run_reference_batch(d, exe, cd, cores, accepted, 2000 + 100 * s)
-            if s >= warmup:
-                tot_p += p
-                tot_w += w
+            t_step, k = 0.0, 0
+            while t_step < per_step * 0.85 or k == 0:
+                p, w = run_reference_batch(d, exe, cd, cores, accepted, 2000 + 1000 * s + 17 * k)
+                t_step += w
+                k += 1
+                if s >= warmup:
+                    tot_p += p
+                    tot_w += w
+                    batches += 1
         return {"value": tot_p / tot_w, "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"{steps} batch(es) of {cores} concurrent unmodified mcmc_eq processes (gcc -O4, one per core), "
-                          f"{accepted} accepted models each, proposal string 'P' on the same synthetic picks: "
+                "sample": f"{batches} batch(es) of {cores} concurrent unmodified mcmc_eq processes (gcc -O4, one per core, fresh "
+                          f"chains of {accepted} accepted models), proposal string 'P' on the same synthetic picks: "
                           f"{tot_p} proposals in {tot_w:.1f} s"}, tot_w
     finally:
         shutil.rmtree(d, ignore_errors=True)
@@ -232,7 +248,7 @@ def cpu_baseline(cfg, pk, truth, budget_s, steps=1, warmup=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=1024, help="chains per GPU")
@@ -244,7 +260,13 @@ def main():
     args = ap.parse_args()
     W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    rank, world, local, dist = dist_setup(args.gpus)
+    if args.impl == "reference":
+        # the reference is a CPU program: rank 0 alone times it, the other ranks leave without joining any group
+        rank, world, local, dist = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), 0, None
+        if rank != 0:
+            return
+    else:
+        rank, world, local, dist = dist_setup(args.gpus)
     n_gpus = max(world, 1)
     workload = (f"synth-{args.chains}: {args.chains} chains/GPU x {args.events} events x {args.stations} stations "
                 f"({2 * args.events * args.stations} picks), Example grid h=2 km 200x200x62 (eikonal plane 282x62), "
@@ -257,9 +279,10 @@ def main():
     from mcmc_eq_b200 import synth
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        cfg, pk, truth = synth.workload(args.events, args.stations, 33, 0)
+        def oracle_predict(cfg, pk0, st):   # synthetic picks without touching the GPU library
+            from tests import fwd_helpers as fh
+            return fh.oracle_forward(cfg, pk0, st["z"], st["vp"], st["vpvs"], st["eq"], st["pres"], st["sres"])[3]
+        cfg, pk, truth = synth.workload(args.events, args.stations, 33, 0, predictor=oracle_predict)
         base, wall = cpu_baseline(cfg, pk, truth, 150.0, steps=max(args.steps, 1), warmup=args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(args.steps, 1), "higher_is_better": True,
@@ -271,7 +294,8 @@ def main():
 
     device = local
     cfg, pk, truth = synth.workload(args.events, args.stations, 33, device, j_max_start=0, j_max_main=2**30, deci=2**30)
-    smp = mq.Sampler(cfg, pk, args.chains, device, 1000 + rank)
+    smp = mq.Sampler(cfg, pk, args.chains, device, 1000)
+    smp.set_chain_offset(rank * args.chains)     # chain g of the job draws from stream (seed, g) on whichever GPU it runs
     smp.init_chains()
     # leave the start phase of the chain the way a real run does: a few hundred mixed iterations are not needed for
     # timing (the cost of a 'P' step does not depend on the state), but the models must be valid chain states
@@ -308,8 +332,9 @@ def main():
         t_launch = eik_ms / eik_n / 1000.0
         achieved = alg_bytes_per_solve * solves_per_launch / t_launch / 1e9
         smem_alg = 32.0 * nxmod * nz * solves_per_launch / t_launch / 1e9
-        roofline = {"bound": "hbm", "kernel": "eik_generic_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        kernel = "eik_generic_kernel" if os.environ.get("MCMCEQ_EIKONAL") == "generic" else "eik_fast_kernel"
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": kernel_traffic(kernel, solves_per_launch), "peak_source": peak_src,
                     "algorithmic_bytes_per_solve": alg_bytes_per_solve, "solves_per_launch": int(solves_per_launch),
                     "avg_launch_ms": eik_ms / eik_n, "share_of_step": eik_ms / ms,
                     "layout": "receiver rows only are stored (3 of 62 rows); algorithmic bytes count the full field as the reference materialises it",

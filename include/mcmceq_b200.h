@@ -226,6 +226,47 @@ int mq_snapshot(mq_handle* h, int chain, int which, mq_record_fn fn, void* user)
 
 int mq_sync(mq_handle* h);
 
+/* ===== more than one GPU =====================================================================================
+ * One process per GPU, chains sharded contiguously (the reference runs chains as independent processes,
+ * run/srun_mcmc_eq.sh:13,35): the data path has no collective.  NCCL appears in two optional places. */
+
+/* Global index of this handle's chain 0.  Chain g of a job draws from the random stream (seed, g) whichever GPU it
+ * runs on, so a run is reproducible under any sharding.  Call before mq_init_chains.  mq_comm_init sets rank*n_chains. */
+int mq_set_chain_offset(mq_handle* h, int64_t first_chain);
+
+/* On-device posterior accumulation = pass 1 of the reference's analyse_eq (src/analyse_eq.c:496-643) applied to every
+ * decimated model (the "mod" records, src/mcmc_eq.c:1163) whose number is > burn_in, as it is produced:
+ *   hist_vp[j*nz + i]   models whose Vp at depth node i falls in bin j, j = (int)((v - vpmin)/dv)   (hcountp, :589-590)
+ *   hist_vpvs[j*nz + i] the same for Vp/Vs (hcounts, :605-606);  boundary[i] models with a layer boundary at node i (:586)
+ *   vsum[i*4 + k]       sums over models of vp, vp^2, vpvs, vpvs^2 at node i (values clipped to the prior range, :587-588)
+ *   eqsum[e*8 + k]      sums of x, y, z, origin time of event e, then of their squares (:619-623)
+ *   ressum[s*4 + k]     sums of the P and S correction of station s, then of their squares (:636-637)
+ *   noisesum[k], noisesum[8 + k]   sums of the eight sigmas (index 2*class+phase) and of their squares (:525-532)
+ * mq_posterior_begin allocates and zeroes the accumulators (dims tells the sizes), mq_posterior_get copies them out
+ * (any pointer may be NULL), mq_posterior_allreduce sums them over all ranks of the communicator in place. */
+typedef struct mq_posterior_dims { int32_t ndv, ndvpvs, nz, n_events, n_stations; } mq_posterior_dims;
+int mq_posterior_begin(mq_handle* h, float dv, float dvpvs, int64_t burn_in, mq_posterior_dims* dims);
+int mq_posterior_get(mq_handle* h, int32_t* hist_vp, int32_t* hist_vpvs, int32_t* boundary, double* vsum, double* eqsum,
+                     double* ressum, double* noisesum, int64_t* n_models);
+int mq_posterior_allreduce(mq_handle* h);
+
+/* NCCL communicator of the job (one rank per handle).  Rank 0 calls mq_comm_unique_id and hands the 128 bytes to the
+ * other ranks by whatever means the host has (torch.distributed broadcast, a file, MPI); every rank then calls
+ * mq_comm_init.  libnccl is bound at run time; MQ_ERR_UNSUPPORTED when it is absent. */
+#define MQ_COMM_ID_BYTES 128
+int mq_comm_unique_id(uint8_t* id);
+int mq_comm_init(mq_handle* h, const uint8_t* id, int rank, int world);
+int mq_comm_destroy(mq_handle* h);
+
+/* Optional parallel tempering (not reference behaviour): chain c samples prior x likelihood^beta[c]; beta == 1 is the
+ * reference's chain.  mq_temper_swap proposes one round of swaps between neighbouring chains of the global numbering
+ * (pairs (2k+p, 2k+1+p), p = round & 1): one all-gather of (log-likelihood, beta) per chain, identical decisions on
+ * every rank from a shared counter-based stream keyed by (seed, round, pair), temperatures are swapped, states stay.
+ * Works without a communicator (single GPU).  *n_swapped counts accepted swaps whose lower chain is on this rank. */
+int mq_set_beta(mq_handle* h, const float* beta);
+int mq_get_beta(mq_handle* h, float* beta);
+int mq_temper_swap(mq_handle* h, int64_t round, int32_t* n_swapped);
+
 /* Measurement aid for bench.py: with enable != 0 every eikonal launch is bracketed by CUDA events on
  * the handle's stream.  Returns the time and number of launches accumulated since the previous call
  * (and restarts the accumulation); solves_per_full_launch = 2 * n_chains * nz, the number of solves one

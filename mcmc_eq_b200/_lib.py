@@ -76,6 +76,10 @@ class MqReplay(C.Structure):
                 ("log_fac", dp), ("u", fp), ("accepted", ip), ("alpha", fp), ("new_ll", dp), ("mf", fp)]
 
 
+class MqPosteriorDims(C.Structure):
+    _fields_ = [("ndv", C.c_int32), ("ndvpvs", C.c_int32), ("nz", C.c_int32), ("n_events", C.c_int32), ("n_stations", C.c_int32)]
+
+
 RECORD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(MqRecord))
 
 
@@ -98,6 +102,17 @@ def lib() -> C.CDLL:
         L.mq_get_models.argtypes = [C.c_void_p, C.POINTER(MqModels)]
         L.mq_forward.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.mq_forward_host.argtypes = [C.c_void_p, C.POINTER(MqModels), C.c_int, fp, fp]
+        u8p = C.POINTER(C.c_uint8)
+        L.mq_set_chain_offset.argtypes = [C.c_void_p, C.c_int64]
+        L.mq_posterior_begin.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int64, C.POINTER(MqPosteriorDims)]
+        L.mq_posterior_get.argtypes = [C.c_void_p, ip, ip, ip, dp, dp, dp, dp, lp]
+        L.mq_posterior_allreduce.argtypes = [C.c_void_p]
+        L.mq_comm_unique_id.argtypes = [u8p]
+        L.mq_comm_init.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int]
+        L.mq_comm_destroy.argtypes = [C.c_void_p]
+        L.mq_set_beta.argtypes = [C.c_void_p, fp]
+        L.mq_get_beta.argtypes = [C.c_void_p, fp]
+        L.mq_temper_swap.argtypes = [C.c_void_p, C.c_int64, ip]
         L.mq_tables_save.argtypes = [C.c_void_p]
         L.mq_tables_restore.argtypes = [C.c_void_p]
         L.mq_get_table.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
@@ -116,6 +131,13 @@ def lib() -> C.CDLL:
         L.mqio_free_picks.argtypes = [C.POINTER(MqioPicks)]
         _lib = L
     return _lib
+
+
+def comm_unique_id() -> bytes:
+    """128 bytes identifying a new NCCL communicator (rank 0 calls this and distributes them)."""
+    buf = (C.c_uint8 * 128)()
+    check(lib().mq_comm_unique_id(buf))
+    return bytes(buf)
 
 
 def check(rc: int) -> None:
@@ -301,6 +323,53 @@ class Sampler:
         r = MqReplay(n, C.cast(kb, C.c_char_p), C.pointer(v), _p(q, ip), _p(lf, dp), _p(uu), _p(acc, ip), _p(alpha), _p(ll, dp), _p(mf))
         check(lib().mq_replay_step(self.h, C.byref(r)))
         return dict(accepted=acc, alpha=alpha, new_ll=ll, mf=mf)
+
+    # ---- more than one GPU / posterior / tempering -------------------------------------------------------
+    def set_chain_offset(self, first_chain: int):
+        check(lib().mq_set_chain_offset(self.h, first_chain))
+
+    def posterior_begin(self, dv: float, dvpvs: float, burn_in: int = 0):
+        d = MqPosteriorDims()
+        check(lib().mq_posterior_begin(self.h, dv, dvpvs, burn_in, C.byref(d)))
+        self._pdims = d
+        return d
+
+    def posterior_get(self):
+        d = self._pdims
+        out = dict(hist_vp=np.zeros((d.ndv, d.nz), np.int32), hist_vpvs=np.zeros((d.ndvpvs, d.nz), np.int32),
+                   boundary=np.zeros(d.nz, np.int32), vsum=np.zeros((d.nz, 4)), eqsum=np.zeros((d.n_events, 8)),
+                   ressum=np.zeros((d.n_stations, 4)), noisesum=np.zeros(16))
+        n = C.c_int64(0)
+        check(lib().mq_posterior_get(self.h, _p(out["hist_vp"], ip), _p(out["hist_vpvs"], ip), _p(out["boundary"], ip),
+                                     _p(out["vsum"], dp), _p(out["eqsum"], dp), _p(out["ressum"], dp), _p(out["noisesum"], dp),
+                                     C.byref(n)))
+        out["n_models"] = n.value
+        return out
+
+    def posterior_allreduce(self):
+        check(lib().mq_posterior_allreduce(self.h))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().mq_comm_init(self.h, buf, rank, world))
+
+    def comm_destroy(self):
+        check(lib().mq_comm_destroy(self.h))
+
+    def set_beta(self, beta):
+        b = _f32(beta)
+        assert b.shape == (self.n,)
+        check(lib().mq_set_beta(self.h, _p(b)))
+
+    def get_beta(self) -> np.ndarray:
+        b = np.zeros(self.n, np.float32)
+        check(lib().mq_get_beta(self.h, _p(b)))
+        return b
+
+    def temper_swap(self, round_: int) -> int:
+        k = C.c_int32(0)
+        check(lib().mq_temper_swap(self.h, round_, C.byref(k)))
+        return k.value
 
     def sync(self):
         check(lib().mq_sync(self.h))

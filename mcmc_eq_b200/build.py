@@ -47,7 +47,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not force and _newer(LIB, deps):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-lcudart"]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True, cwd=ROOT)
     return LIB
 

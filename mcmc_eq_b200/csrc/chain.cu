@@ -130,6 +130,7 @@ struct SamplerParams {
     int n_class[8];
     uint64_t seed;
     size_t tab_stride;
+    long long chain_offset;
 };
 
 static SamplerParams make_params(const Handle* h)
@@ -141,7 +142,7 @@ static SamplerParams make_params(const Handle* h)
     p.revert = (int)(h->cfg.j_max_start + h->cfg.j_max_main / 2);   // src/mcmc_eq.c:840
     p.sum_of_picks = h->sum_of_picks;
     for (int k = 0; k < 8; k++) p.n_class[k] = h->n_class[k];
-    p.seed = h->seed; p.tab_stride = h->tab_stride;
+    p.seed = h->seed; p.tab_stride = h->tab_stride; p.chain_offset = h->chain_offset;
     return p;
 }
 
@@ -203,7 +204,7 @@ __global__ void init_chains_kernel(SamplerParams p, Handle hd, SamplerDev s)
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.n) return;
     const mq_config& g = p.cfg;
-    Philox rng(p.seed, (uint32_t)c, 0);
+    Philox rng(p.seed, (uint32_t)(p.chain_offset + c), 0);
     bool ok = true;
     const float inv = (g.inv_control > 0.f) ? -g.inv_control : g.inv_control;
     s.inv_control[c] = inv;
@@ -266,7 +267,7 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
     const long j = (long)s.acce[c];
     if (j >= (long)g.j_max_start + (long)g.j_max_main) return;   // chain finished (src/mcmc_eq.c:845)
 
-    Philox rng(p.seed, (uint32_t)c, s.draws[c]);
+    Philox rng(p.seed, (uint32_t)(p.chain_offset + c), s.draws[c]);
     float inv = s.inv_control[c];
     if (j == p.revert && p.lvz_flag == 1) { inv = -inv; s.inv_control[c] = inv; }   // fires every iteration while acce == revert (:849-853)
 
@@ -497,7 +498,11 @@ __global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView
         new_misfit = chain_misfit(mf, noise);
         new_rms = chain_rms(mf, p.sum_of_picks);
         new_ll = -new_misfit / 2.0;
-        alpha = chain_alpha(s.log_fac[c], new_ll, hd.ll[c]);
+        // parallel tempering (comm.cu): the likelihood enters with the chain's inverse temperature; for the noise arm
+        // log_fac is the likelihood's normalisation term (src/mcmc_eq.c:1114-1117) and is tempered with it.  beta == 1
+        // (the default, and the reference) leaves every operand unchanged.
+        const double beta = hd.beta ? (double)hd.beta[c] : 1.0;
+        alpha = chain_alpha((kind == 'N') ? beta * s.log_fac[c] : s.log_fac[c], beta * new_ll, beta * hd.ll[c]);
         cnt[0]++;   // nmod: models whose misfit was evaluated
     }
     if (g.aflag == 1) alpha = 1.f;
@@ -506,7 +511,7 @@ __global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView
     float u;
     if (s.u_inject) u = s.u_inject[c];   // replay: the reference's own deviate, no draw is consumed
     else {
-        Philox rng(p.seed, (uint32_t)c, s.draws[c]);
+        Philox rng(p.seed, (uint32_t)(p.chain_offset + c), s.draws[c]);
         u = rng.uniform();
         s.draws[c] = rng.draws;
     }
@@ -586,10 +591,66 @@ __device__ void snapshot_copy(const SamplerParams& p, const Handle& hd, const Sn
     if (threadIdx.x == 0) d.dim[c] = dim;
 }
 
+// analyse_eq pass 1 for one decimated model (src/analyse_eq.c:564-640): per depth node the velocity of the nearest
+// nucleus, clipped to the prior range, goes into the Vp and Vp/Vs histograms; hypocentres, origin times, station
+// corrections and sigmas into running sums.
+__device__ void posterior_accumulate(const SamplerParams& p, const Handle& hd, int c)
+{
+    const Posterior& P = hd.post;
+    const int n = p.n, mc = hd.mcur[c], ec = hd.ecur[c];
+    const int dim = hd.dim[mc * n + c];
+    const size_t mo = ((size_t)mc * n + c) * p.md;
+    const float* z = hd.z + mo; const float* vp = hd.vp + mo; const float* vpvs = hd.vpvs + mo;
+    int32_t* hist_vp = P.iblock;
+    int32_t* hist_vs = hist_vp + (size_t)P.ndv * p.nz;
+    int32_t* boundary = hist_vs + (size_t)P.ndvpvs * p.nz;
+    double* vsum = P.dblock;
+    double* eqsum = vsum + 4 * (size_t)p.nz;
+    double* ressum = eqsum + 8 * (size_t)p.ne;
+    double* noisesum = ressum + 4 * (size_t)p.ns;
+    const mq_config& g = p.cfg;
+    for (int i = threadIdx.x; i < p.nz; i += blockDim.x) {
+        const float zz = __fadd_rn(__fmul_rn((float)i, g.grid.h), g.grid.z0);
+        const int k = find_in_cell_dev(z, dim, zz);
+        float vv = vp[k];
+        const float vvx = vp[find_in_cell_dev(z, dim, __fsub_rn(zz, g.grid.h))];
+        if (vv != vvx) atomicAdd(&boundary[i], 1);
+        if (vv > g.vpmax) vv = g.vpmax;
+        if (vv < g.vpmin) vv = g.vpmin;
+        int j = (int)__fdiv_rn(__fsub_rn(vv, g.vpmin), P.dv);
+        if (j > P.ndv - 1) j = P.ndv - 1;
+        atomicAdd(&hist_vp[(size_t)j * p.nz + i], 1);
+        float rr = vpvs[k];
+        if (rr > g.vpvsmax) rr = g.vpvsmax;
+        if (rr < g.vpvsmin) rr = g.vpvsmin;
+        j = (int)__fdiv_rn(__fsub_rn(rr, g.vpvsmin), P.dvpvs);
+        if (j > P.ndvpvs - 1) j = P.ndvpvs - 1;
+        atomicAdd(&hist_vs[(size_t)j * p.nz + i], 1);
+        atomicAdd(&vsum[4 * i], (double)vv); atomicAdd(&vsum[4 * i + 1], (double)vv * vv);
+        atomicAdd(&vsum[4 * i + 2], (double)rr); atomicAdd(&vsum[4 * i + 3], (double)rr * rr);
+    }
+    for (int e = threadIdx.x; e < p.ne; e += blockDim.x) {
+        const float* q = hd.eq + ((size_t)c * p.ne + e) * 3;
+        const double v[4] = {q[0], q[1], q[2], hd.origin[((size_t)ec * n + c) * p.ne + e]};
+        for (int k = 0; k < 4; k++) { atomicAdd(&eqsum[8 * e + k], v[k]); atomicAdd(&eqsum[8 * e + 4 + k], v[k] * v[k]); }
+    }
+    for (int i = threadIdx.x; i < p.ns; i += blockDim.x) {
+        const double a = hd.pres[(size_t)c * p.ns + i], b = hd.sres[(size_t)c * p.ns + i];
+        atomicAdd(&ressum[4 * i], a); atomicAdd(&ressum[4 * i + 1], b);
+        atomicAdd(&ressum[4 * i + 2], a * a); atomicAdd(&ressum[4 * i + 3], b * b);
+    }
+    if (threadIdx.x < 8) {
+        const double v = hd.noise[8 * (size_t)c + threadIdx.x];
+        atomicAdd(&noisesum[threadIdx.x], v); atomicAdd(&noisesum[8 + threadIdx.x], v * v);
+    }
+    if (threadIdx.x == 0) atomicAdd(&noisesum[16], 1.0);
+}
+
 __global__ void snapshot_kernel(SamplerParams p, Handle hd, SamplerDev s)
 {
     const int c = blockIdx.x;
     if (s.out.flag[c] >= 2) {
+        if (hd.post.on && (long long)s.out.number[c] > hd.post.burn_in) posterior_accumulate(p, hd, c);
         snapshot_copy(p, hd, s.out, c);
         __syncthreads();
         if (threadIdx.x == 0) s.out.flag[c] = 1;   // 1 = ready for mq_drain

@@ -37,6 +37,7 @@ __host__ __device__ inline float chain_alpha(double log_fac, double new_ll, doub
 }
 
 void sampler_destroy(Handle* h);
+void comm_destroy(Handle* h);
 int forward_current_device(Handle* h, int calct);
 
 }  // namespace mq

@@ -47,6 +47,18 @@ struct EvalView {
     float* sres_over;
 };
 
+// On-device posterior accumulation = pass 1 of the reference's analyse_eq (src/analyse_eq.c:496-643) applied to every
+// decimated model as it is produced.  Two contiguous blocks so that the cross-GPU reduction is one all-reduce each.
+struct Posterior {
+    int on;
+    float dv, dvpvs;
+    int ndv, ndvpvs;
+    long long burn_in;      // models with number <= burn_in are skipped (the scripts' `$3 > bi` filter)
+    int32_t* iblock;        // hist_vp [ndv][nz] | hist_vpvs [ndvpvs][nz] | boundary [nz]
+    double* dblock;         // vsum [nz][4] | eqsum [ne][8] | ressum [ns][4] | noisesum [16] | n_models [1]
+    size_t n_int, n_dbl;
+};
+
 struct Handle {
     mq_config cfg;
     int device;
@@ -100,6 +112,12 @@ struct Handle {
 
     // optional timing of the dominant kernel (mq_profile): CUDA events round every eikonal launch
     void* prof;
+
+    // multi-GPU (comm.cu): global index of chain 0, inverse temperatures, NCCL communicator, posterior accumulators
+    long long chain_offset;
+    float* beta;         // [n] or nullptr (all 1)
+    void* comm;
+    Posterior post;
 };
 
 }  // namespace mq

@@ -80,3 +80,19 @@ def write_picks(pk, path: str, t64=None) -> None:
                 ph = "P" if (j - b) < n_p[e] else "S"
                 f.write(f"S{int(a['st_id'][j]):03d} {int(a['st_id'][j]):03d} {ph} {a['x'][j]:8.3f} {a['y'][j]:8.3f} "
                         f"{a['z'][j]:8.3f} {t[j]:8.3f} {int(a['cls'][j])}\n")
+
+
+def format_record(rec: dict, reftime, tag: str = "mod") -> str:
+    """Text of one record as print_model_raw writes it (src/mcmc_eq.c:234-248; C twin: host/mq_io.c mqio_write_record).
+    `rec` is a record dict of Sampler.drain() / Sampler.snapshot()."""
+    code = {"mod": rec["code"] + ".", "sta": "ST", "bat": "BF"}[tag]
+    n, rms = rec["noise"], float(np.float32(rec["rms"]))
+    out = ["%3s %2s %8d %3d %f" % (tag, code, rec["number"], rec["dim"], rms) +
+           "".join(" %f" % float(n[k]) for k in (0, 2, 4, 6, 1, 3, 5, 7)) +
+           "".join(" %f %f %f" % (float(rec["z"][i]), float(rec["vp"][i]), float(rec["vpvs"][i])) for i in range(rec["dim"]))]
+    for i, q in enumerate(rec["eq"]):
+        out.append("EQ  %2s %8d %d %f %f %f %f %f %f" % (code, rec["number"], i, rms, float(q[0]), float(q[1]), float(q[2]),
+                                                       float(reftime[i]), float(rec["origin"][i])))
+    for i in range(len(rec["pres"])):
+        out.append("RES %2s %8d %d %f %f %f" % (code, rec["number"], i, rms, float(rec["pres"][i]), float(rec["sres"][i])))
+    return "\n".join(out) + "\n"

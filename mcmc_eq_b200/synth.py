@@ -61,22 +61,29 @@ def picks_from(geo, t=None) -> Picks:
     return Picks(ev_off, np.full(ne, ns, np.int32), st, x, y, z, tt, cls, np.arange(ne) * 1000.0, None, ns)
 
 
-def workload(n_events: int = 200, n_stations: int = 50, seed: int = 33, device: int = 0, rms: float = 0.10, **cfg_override):
-    """-> (config, picks, truth) with travel times predicted from the truth model on the GPU + noise."""
+def workload(n_events: int = 200, n_stations: int = 50, seed: int = 33, device: int = 0, rms: float = 0.10, predictor=None,
+             **cfg_override):
+    """-> (config, picks, truth) with travel times predicted from the truth model + noise.  The prediction comes from the
+    GPU library, or from `predictor(cfg, picks, truth_state) -> t_pred[n_picks]` when given (bench.py's reference arm
+    passes the CPU oracle there so that nothing of this library runs in that arm)."""
     cfg = config(**cfg_override)
     geo = geometry(n_events, n_stations, seed)
     pk0 = picks_from(geo)
-    s = Sampler(cfg, pk0, 1, device, seed)
-    m = s.new_models()
-    d = len(TRUTH_Z)
-    m.dim[0] = d
-    m.z[0, :d], m.vp[0, :d], m.vpvs[0, :d] = TRUTH_Z, TRUTH_VP, TRUTH_VPVS
-    m.eq[0] = geo["ev"]
-    m.pres[0], m.sres[0] = geo["pcor"], geo["scor"]
-    s.set_models(m)
-    s.forward(3)
-    _res, tpred = s.predictions(0)
-    s.close()
+    if predictor is not None:
+        tpred = np.asarray(predictor(cfg, pk0, dict(z=TRUTH_Z, vp=TRUTH_VP, vpvs=TRUTH_VPVS, eq=geo["ev"], pres=geo["pcor"],
+                                                   sres=geo["scor"])), np.float32)
+    else:
+        s = Sampler(cfg, pk0, 1, device, seed)
+        m = s.new_models()
+        d = len(TRUTH_Z)
+        m.dim[0] = d
+        m.z[0, :d], m.vp[0, :d], m.vpvs[0, :d] = TRUTH_Z, TRUTH_VP, TRUTH_VPVS
+        m.eq[0] = geo["ev"]
+        m.pres[0], m.sres[0] = geo["pcor"], geo["scor"]
+        s.set_models(m)
+        s.forward(3)
+        _res, tpred = s.predictions(0)
+        s.close()
     ns = n_stations
     is_s = np.tile(np.repeat([0.0, 1.0], ns), n_events)
     cls = geo["cls"].reshape(-1)
