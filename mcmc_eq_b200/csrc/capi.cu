@@ -119,7 +119,7 @@ extern "C" int mq_destroy(mq_handle* hh)
     free_view(&h->cur_view); free_view(&h->prop_view);
     cudaFree(h->evq); cudaFree(h->oq); cudaFree(h->mf_eval); cudaFree(h->resid); cudaFree(h->tpred);
     cudaFree(h->item_chain); cudaFree(h->item_phase); cudaFree(h->n_items); cudaFree(h->slow); cudaFree(h->item_tab);
-    cudaFree(h->solve_status); cudaFree(h->scratch);
+    cudaFree(h->solve_status); cudaFree(h->scratch); cudaFree(h->eik_order); cudaFree(h->eik_order_work);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete hh;
     return MQ_OK;
@@ -238,6 +238,16 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
         warps = (warps + 3) / 4 * 4;
         h->scratch_warps = (int)warps;
         TRY(cudaMalloc(&h->scratch, (size_t)warps * eik_scratch_floats_per_warp(h->nxmod, h->nz) * sizeof(float)));
+    }
+    {
+        // regrouping of the solves of a table rebuild (MCMCEQ_EIKONAL_ORDER=0 keeps the natural order)
+        const char* e = getenv("MCMCEQ_EIKONAL_ORDER");
+        if (!(e && e[0] == '0') && eik_fast_supported(h->nxmod, h->nz)) {
+            const int max_solves = 2 * n_chains * h->nz;
+            h->eik_order_bytes = eik_order_bytes(max_solves);
+            TRY(cudaMalloc(&h->eik_order_work, h->eik_order_bytes));
+            TRY(cudaMalloc((void**)&h->eik_order, (((size_t)max_solves + 31) / 32 * 32) * sizeof(int32_t)));
+        }
     }
     TRY(cudaStreamSynchronize(s));
 #undef TRY

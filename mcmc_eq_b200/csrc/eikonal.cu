@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "launch_count.h"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace mq {
 
@@ -104,9 +105,10 @@ __global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims 
     const int n_tasks = (n_solves + 31) >> 5;
 
     for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const int g = task * 32 + lane;
+        int g = task * 32 + lane;
+        if (b.order) g = b.order[g];
         eikf::LaneTask t;
-        t.valid = g < n_solves;
+        t.valid = g >= 0 && g < n_solves;
         t.iz = 0; t.slow = nullptr; t.out = nullptr; t.out_rstride = 0; t.full = nullptr;
         if (t.valid) {
             int item;
@@ -127,6 +129,81 @@ __global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims 
         }
         __syncwarp();
     }
+}
+
+// ---- regrouping of solves --------------------------------------------------------------------------------------
+// What a solve does before its march is decided by the layering round its source: the half-width of the
+// quasi-homogeneous box (distance to the nearest interface above and below, src/time_2d.c:598-644) selects the kind
+// of initialisation and the size of the seed box, the next interfaces decide when rows start to carry head waves.
+// Key = source depth (major, so that the lanes of a warp share the box schedule), then those distances.
+__global__ void eik_key_kernel(EikBatch b, int max_solves, uint64_t* keys, int32_t* vals)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= max_solves) return;
+    const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
+    const int n_solves = n_items * b.nz;
+    if (g >= n_solves) { keys[g] = ~0ull; vals[g] = -1; return; }
+    const int iz = g / n_items, item = g - iz * n_items;
+    const float* s = b.slow + (size_t)item * b.nz;
+    const int my = b.nz - 1;
+    const int ysc = (iz == my) ? iz - 1 : iz;
+    const float hs0 = s[ysc], tol = hs0 * 0.001f;
+    // run lengths of the layering seen from the source cell: three layers below and above, 5 bits each
+    // (thickness in cells capped at 15, and whether the next layer is faster); 31 = the model ends there
+    auto runs = [&](int dir, int last, uint64_t* f) {
+        int y = ysc;
+        float ref = hs0;
+        bool ended = false;
+        for (int layer = 0; layer < 3; layer++) {
+            if (ended) { f[layer] = 31; continue; }
+            int len = 0;
+            while (y != last && fabsf(s[y + dir] - ref) <= tol) { y += dir; if (len < 15) len++; }
+            if (y == last) { f[layer] = 31; ended = true; continue; }
+            const int faster = s[y + dir] < ref;
+            ref = s[y + dir];
+            y += dir;
+            f[layer] = (uint64_t)(len << 1 | faster);
+        }
+    };
+    uint64_t dn[3], up[3];
+    runs(+1, my - 1, dn);
+    runs(-1, 0, up);
+    const uint64_t d0 = dn[0], d1 = dn[1], d2 = dn[2], u0 = up[0], u1 = up[1], u2 = up[2];
+    // half-width of the seed box first: it decides the kind of initialisation (src/time_2d.c:682-711)
+    const uint64_t wd = (d0 == 31) ? 15 : (d0 >> 1), wu = (u0 == 31) ? 15 : (u0 >> 1), w = wd < wu ? wd : wu;
+    (void)u2;
+    keys[g] = ((uint64_t)iz << 32) | (w << 28) | (d0 << 23) | (u0 << 18) | (d1 << 13) | (u1 << 8) | (d2 << 3);
+    vals[g] = g;
+}
+
+size_t eik_order_bytes(int max_solves)
+{
+    const size_t n = ((size_t)max_solves + 31) / 32 * 32;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)n, 0, 44);
+    return 2 * n * sizeof(uint64_t) + n * sizeof(int32_t) + ((tmp + 255) / 256 * 256) + 1024;
+}
+
+cudaError_t eik_order_tasks(const EikBatch& b, int32_t* order, void* work, size_t work_bytes, cudaStream_t stream)
+{
+    const int max_solves = b.n_items * b.nz;
+    if (max_solves <= 0) return cudaSuccess;
+    const size_t n = ((size_t)max_solves + 31) / 32 * 32;
+    char* w = (char*)work;
+    uint64_t* k_in = (uint64_t*)w;               w += n * sizeof(uint64_t);
+    uint64_t* k_out = (uint64_t*)w;              w += n * sizeof(uint64_t);
+    int32_t* v_in = (int32_t*)w;                 w += n * sizeof(int32_t);
+    w = (char*)(((uintptr_t)w + 255) / 256 * 256);
+    size_t tmp = work_bytes - (size_t)(w - (char*)work);
+    eik_key_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(b, (int)n, k_in, v_in);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // source depth needs at most 12 bits above bit 32 (nz <= 4096)
+    e = cub::DeviceRadixSort::SortPairs(w, tmp, k_in, k_out, v_in, order, (int)n, 0, 44, stream);
+    count_launch(3);
+    return e;
 }
 
 int eik_fast_max_warps(int nxmod, int nz, int device)

@@ -20,6 +20,10 @@ struct EikBatch {
                                 // (n_items is then the upper bound the grid is sized for)
     const int32_t* src_iz;    // [n_solves] device or nullptr
     int n_solves;
+    // Table mode only: optional execution order.  order[j] = the solve (iz * n_items + item) that lane j % 32 of warp
+    // task j / 32 runs, or -1 (eik_order_tasks fills it: solves of one source depth that initialise and grow their
+    // boxes alike are made neighbours so that the lanes of a warp stay in step).
+    const int32_t* order;
     // Outputs (device).  full_out: [n_solves][nxmod*nz] in the reference layout (x*nz+y).
     float* full_out;
     // Receiver-row tables: table of item i starts at row_out[i] (or row_out_base + i*row_item_stride
@@ -47,6 +51,10 @@ bool eik_fast_supported(int nxmod, int nz);
 cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream);
 // Picks the fast kernel when the grid allows it (MCMCEQ_EIKONAL=generic forces the generic one).
 cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream);
+// Regrouping of the solves of a table-mode batch (see EikBatch::order).  `work` holds the sort buffers:
+// eik_order_bytes(max_solves) bytes.  Fills order[0 .. round_up(max_solves, 32)).
+size_t eik_order_bytes(int max_solves);
+cudaError_t eik_order_tasks(const EikBatch& b, int32_t* order, void* work, size_t work_bytes, cudaStream_t stream);
 // resident warps the fast kernel can use on this device (for sizing the scratch)
 int eik_fast_max_warps(int nxmod, int nz, int device);
 

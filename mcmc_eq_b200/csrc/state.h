@@ -106,6 +106,9 @@ struct Handle {
     int32_t* solve_status; // [1] min over solves
     float* scratch;      // eikonal scratch
     int scratch_warps;
+    int32_t* eik_order;  // [round_up(2n*nz, 32)] execution order of the solves of a table rebuild (eikonal.cuh), or nullptr
+    void* eik_order_work;
+    size_t eik_order_bytes;
 
     // sampler (chain.cu)
     void* sampler;
