@@ -437,12 +437,57 @@ EIK_HD bool march_sweep2(bool act, const float* P, float* C, const float* S, int
 // loop iteration as two independent dependency chains -- twice the instruction-level parallelism per warp, which is
 // what a kernel limited to ~2 warps per scheduler by its shared-memory footprint needs -- and meet in the middle;
 // whoever reaches a node second merges with fminf.  Same values as march_sweep2, bit for bit.
+// One node of each chain.  A: node k timed from k-1 (state: past times of k-1 and k, cell k-1, current time of k-1);
+// B: node k timed from k+1.  Both also time the roots they pass (1-D transmission) so that neither waits for the other.
+struct ChainA { float pprev, pk, sprev, cn; };
+struct ChainB { float pnx, pk, s0, cn; };
+
+EIK_HD float chain_a_node(ChainA& a, float pnext, float sk, bool& tie)
+{
+    const float dt = a.pk - a.pprev;
+    const bool up = dt >= 0.f;
+    const bool root = !up && (pnext >= a.pk);
+    tie = tie || (dt == 0.f);
+    const float lim = a.sprev * kRsqrt2;
+    const float s0sq = a.sprev * a.sprev;
+    float est = a.pk + sqrt_pos(fmaf(-dt, dt, s0sq));
+    float cv = (dt < lim) ? est : kInf;
+    const float dt2 = a.cn - a.pprev;
+    est = a.cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
+    cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+    cv = fminf(cv, a.pk + sk);
+    cv = fminf(cv, fmaf(a.sprev, kSqrt2, a.pprev));
+    const float cmin = fminf(kInf, a.pk + eik::fmin_ref(a.sprev, sk));
+    const float val = up ? cv : (root ? cmin : kInf);
+    a.cn = val; a.pprev = a.pk; a.pk = pnext; a.sprev = sk;
+    return val;
+}
+
+EIK_HD float chain_b_node(ChainB& b, float pprev, float hs1)
+{
+    const float dt = b.pk - b.pnx;
+    const bool down = dt >= 0.f;
+    const bool root = (b.pk < pprev) && !down;
+    const float lim = b.s0 * kRsqrt2;
+    const float s0sq = b.s0 * b.s0;
+    float est = b.pk + sqrt_pos(fmaf(-dt, dt, s0sq));
+    float cv = (dt < lim) ? est : kInf;
+    const float dt2 = b.cn - b.pnx;
+    est = b.cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
+    cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+    cv = fminf(cv, b.pk + hs1);
+    cv = fminf(cv, fmaf(b.s0, kSqrt2, b.pnx));
+    const float cmin = fminf(kInf, b.pk + eik::fmin_ref(hs1, b.s0));
+    const float val = down ? cv : (root ? cmin : kInf);
+    b.cn = val; b.pnx = b.pk; b.pk = pprev; b.s0 = hs1;
+    return val;
+}
+
 EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int ke)
 {
     bool tie = false;
-    // chain A state: node ka, parent ka-1;  chain B state: node kb, parent kb+1
-    float a_pprev = kEdge, a_pk = P[0], a_sprev = kInf, a_cn = kInf;
-    float b_pnx = kEdge, b_pk = P[(long)ke * LS], b_s0 = kInf, b_cn = kInf;
+    ChainA a{kEdge, P[0], kInf, kInf};
+    ChainB b{kEdge, P[(long)ke * LS], kInf, kInf};
     const float* pa = P + LS;                 // &P[ka + 1]
     const float* sa = S;                      // &S[ka]
     float* ca = C;                            // &C[ka]
@@ -452,51 +497,10 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
 
     // one node of each chain; MERGE: the other chain has already been at these nodes
     auto step = [&](auto merge) {
-        // ---- A: roots and nodes timed from above
-        float a_val;
-        {
-            const float pnext = *pa;
-            const float sk = *sa;
-            const float dt = a_pk - a_pprev;
-            const bool up = dt >= 0.f;
-            const bool root = !up && (pnext >= a_pk);
-            tie = tie || (dt == 0.f);
-            const float lim = a_sprev * kRsqrt2;
-            const float s0sq = a_sprev * a_sprev;
-            float est = a_pk + sqrt_pos(fmaf(-dt, dt, s0sq));
-            float cv = (dt < lim) ? est : kInf;
-            const float dt2 = a_cn - a_pprev;
-            est = a_cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
-            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
-            cv = fminf(cv, a_pk + sk);
-            cv = fminf(cv, fmaf(a_sprev, kSqrt2, a_pprev));
-            const float cmin = fminf(kInf, a_pk + eik::fmin_ref(a_sprev, sk));
-            a_val = up ? cv : (root ? cmin : kInf);
-            a_cn = a_val; a_pprev = a_pk; a_pk = pnext; a_sprev = sk;
-        }
+        float a_val = chain_a_node(a, *pa, *sa, tie);
         if (decltype(merge)::value) a_val = fminf(a_val, *ca);
         *ca = a_val;
-        // ---- B: roots and nodes timed from below
-        float b_val;
-        {
-            const float pprev = *pb;
-            const float hs1 = *sb;
-            const float dt = b_pk - b_pnx;
-            const bool down = dt >= 0.f;
-            const bool root = (b_pk < pprev) && !down;
-            const float lim = b_s0 * kRsqrt2;
-            const float s0sq = b_s0 * b_s0;
-            float est = b_pk + sqrt_pos(fmaf(-dt, dt, s0sq));
-            float cv = (dt < lim) ? est : kInf;
-            const float dt2 = b_cn - b_pnx;
-            est = b_cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
-            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
-            cv = fminf(cv, b_pk + hs1);
-            cv = fminf(cv, fmaf(b_s0, kSqrt2, b_pnx));
-            const float cmin = fminf(kInf, b_pk + eik::fmin_ref(hs1, b_s0));
-            b_val = down ? cv : (root ? cmin : kInf);
-            b_cn = b_val; b_pnx = b_pk; b_pk = pprev; b_s0 = hs1;
-        }
+        float b_val = chain_b_node(b, *pb, *sb);
         if (decltype(merge)::value) b_val = fminf(b_val, *cb);
         *cb = b_val;
         pa += LS; sa += LS; ca += LS; pb -= LS; sb -= LS; cb -= LS;
@@ -556,8 +560,11 @@ EIK_HD int slow_line(float* t, const Box& b, const Medium& m, const Lane& L, int
 // FINE selects the medium type of the slow path.  out/rows: receiver-row output of the coarse grid
 // (nullptr on the refined grid); out[r*out_rstride + x] receives t[x][rows[r]].
 template <bool FINE>
+// hand_col/hand_x1 (coarse grid only, may be nullptr): split mode.  A lane whose box spans the whole depth range
+// writes its right column (hand_col[k*32], k = 0..my) and X1 there and stops; a separate kernel marches on from it.
 EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMedium& cm, int j0, int hy, float* out,
-                    long out_rstride, const int* rows, int n_rows, float* full, int* xbox_end)
+                    long out_rstride, const int* rows, int n_rows, float* full, int* xbox_end, float* hand_col = nullptr,
+                    int* hand_x1 = nullptr)
 {
     float* T = FINE ? L.WF : L.W;
     Med med;
@@ -573,6 +580,13 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
     if (xbox_end) *xbox_end = boxphase ? -1 : b.X1;
     // cell slowness of a row strip, with the masked dummy row of the coarse grid
     auto rowS = [&](int cy) -> float { return (!FINE && cy >= b.my) ? kInf : med.cell(cy); };
+    const bool split = !FINE && hand_x1 != nullptr;
+    auto hand_over = [&]() {     // this lane's box phase is over: the march kernel takes the column from here
+        for (int k = 0; k <= b.my; k++) hand_col[(size_t)k * 32] = col[(size_t)k * LS];
+        *hand_x1 = b.X1;
+        b.active = 0;
+    };
+    if (split && b.active && !boxphase) hand_over();
 
     for (;;) {
         bool moved = false;
@@ -696,6 +710,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
         if (b.active && boxphase && b.Y0 == 0 && b.Y1 == b.my) {
             boxphase = false;            // from here on the solve is a march over columns
             if (xbox_end) *xbox_end = b.X1;
+            if (split) hand_over();
         }
         if (!EIKF_ANY(moved)) break;
     }
@@ -713,6 +728,8 @@ struct LaneTask {
     float* out;          // receiver rows: out[r*out_rstride + x] = t[x][rows[r]]  (or nullptr)
     long out_rstride;
     float* full;         // whole field in the reference layout x*nz+y (or nullptr)
+    float* hand_col;     // split mode: where the box phase leaves its last column (element k at [k*32]) ...
+    int* hand_x1;        // ... and the column index it belongs to (-1: nothing left to march); nullptr = fused mode
 };
 
 EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int* rows, int n_rows)
@@ -786,7 +803,9 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     // ---- coarse grids
     int xbox_end = -1;
     {
-        const int rc = run_grid<false>(bc, L, D, cm, 0, 0, t.out, t.out_rstride, rows, n_rows, t.full, &xbox_end);
+        if (t.hand_x1) *t.hand_x1 = -1;
+        const int rc = run_grid<false>(bc, L, D, cm, 0, 0, t.out, t.out_rstride, rows, n_rows, t.full, &xbox_end, t.hand_col,
+                                       t.hand_x1);
         if (rc != eik::kOk) status = rc;
     }
     // ---- the part of the output that was computed while the box was still growing (it may have been

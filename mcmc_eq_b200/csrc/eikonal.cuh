@@ -24,6 +24,11 @@ struct EikBatch {
     // task j / 32 runs, or -1 (eik_order_tasks fills it: solves of one source depth that initialise and grow their
     // boxes alike are made neighbours so that the lanes of a warp stay in step).
     const int32_t* order;
+    // Table mode only: split execution (eik_launch_split).  The box kernel leaves, for the lane at position j of the
+    // execution order, its last column in hand_col[((j/32)*nz + k)*32 + j%32] and that column's index in hand_x1[j]
+    // (-1: nothing left to march); the march kernel continues from there.  Both nullptr: one fused kernel.
+    float* hand_col;
+    int32_t* hand_x1;
     // Outputs (device).  full_out: [n_solves][nxmod*nz] in the reference layout (x*nz+y).
     float* full_out;
     // Receiver-row tables: table of item i starts at row_out[i] (or row_out_base + i*row_item_stride
@@ -49,6 +54,11 @@ cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream);
 // is smaller (box window + refined grid) so the generic kernel's scratch always suffices.
 bool eik_fast_supported(int nxmod, int nz);
 cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream);
+// Box phase and march as two kernels, the march with its columns in tensor memory (eik_march.cuh).  Needs
+// b.hand_col / b.hand_x1, receiver-row output only (no full_out), nz <= 254.
+bool eik_split_supported(int nxmod, int nz);
+size_t eik_hand_floats(int max_solves, int nz);
+cudaError_t eik_launch_split(const EikBatch& b, cudaStream_t stream);
 // Picks the fast kernel when the grid allows it (MCMCEQ_EIKONAL=generic forces the generic one).
 cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream);
 // Regrouping of the solves of a table-mode batch (see EikBatch::order).  `work` holds the sort buffers:

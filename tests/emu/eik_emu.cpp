@@ -26,7 +26,7 @@ extern "C" int emu_fast_time_2d(const float* s, int nx, int ny, int iz, float* t
     eikf::carve_shared(SM.data(), D, &L);
     L.W = W.data(); L.WF = WF.data();
     eikf::LaneTask task;
-    task.valid = true; task.iz = iz; task.slow = s; task.out = rows_out; task.out_rstride = nx; task.full = t;
+    task.valid = true; task.iz = iz; task.slow = s; task.out = rows_out; task.out_rstride = nx; task.full = t; task.hand_col = nullptr; task.hand_x1 = nullptr;
     return eikf::solve_warp(D, L, task, rows, n_rows);
 }
 #ifdef EIKF_STATS

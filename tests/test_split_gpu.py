@@ -1,0 +1,52 @@
+"""The optional two-kernel eikonal path (MCMCEQ_EIKONAL_SPLIT=1): box phase in shared memory, column march with its
+columns in tensor memory (csrc/eik_march.cuh: tcgen05.ld/st, 32x32b).  Same arithmetic as the fused kernel, so the class
+sums, origin times and per-pick predictions must be IDENTICAL bit for bit; run in a subprocess because the switch is read
+once per process."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+SCRIPT = r"""
+import sys, tempfile, numpy as np
+sys.path.insert(0, %r)
+import mcmc_eq_b200 as mq
+from tests import inputs, fwd_helpers as fh
+out = {}
+for name in ("example2", "example"):
+    d = tempfile.mkdtemp(prefix="mqsp_")
+    cfgp, pkp = inputs.materialise(name, d)
+    cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
+    n = 70                                        # not a multiple of 32: ragged last warp
+    smp = mq.Sampler(cfg, pk, n, 0, 1)
+    rng = np.random.default_rng(4)
+    st = fh.random_states(rng, cfg, pk, n, kind="posterior") if name == "example" else fh.random_states(rng, cfg, pk, n, kind="lvz")
+    mf, org = smp.forward_host(fh.fill_models(smp.new_models(32), st), 3)
+    res, tp = smp.predictions(3)
+    smp.init_chains(); smp.step(12, "PVMBDQ")
+    c, ll, rms = smp.stats()
+    out[name + "_mf"] = mf; out[name + "_org"] = org; out[name + "_tp"] = tp; out[name + "_ll"] = ll; out[name + "_c"] = c
+    smp.close()
+np.savez(sys.argv[1], **out)
+"""
+
+
+def _run(path, split):
+    env = dict(os.environ, MCMCEQ_EIKONAL_SPLIT="1" if split else "0")
+    r = subprocess.run([sys.executable, "-c", SCRIPT % util.ROOT, path], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    return dict(np.load(path))
+
+
+def test_tensor_memory_march_is_bit_identical_to_the_fused_kernel(tmp_path):
+    a = _run(str(tmp_path / "fused.npz"), False)
+    b = _run(str(tmp_path / "split.npz"), True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.isfinite(a["example_mf"]).all() and a["example2_c"][:, 17].sum() > 0
