@@ -235,6 +235,14 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const long need = ((long)2 * n * h->nz + 31) / 32;
         long warps = std::min<long>(need, (long)sms * 16);
+        // large planes (the 0.1 km fine-grid case: 565 x 2001 nodes = 145 MB per warp): never more than a quarter of the
+        // free device memory; the kernels loop over the tasks with however many warps they are given
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t per_warp = eik_scratch_floats_per_warp(h->nxmod, h->nz) * sizeof(float);
+            const long by_mem = (long)((free_b / 4) / per_warp);
+            warps = std::min<long>(warps, std::max<long>(by_mem, 4));
+        }
         warps = (warps + 3) / 4 * 4;
         h->scratch_warps = (int)warps;
         TRY(cudaMalloc(&h->scratch, (size_t)warps * eik_scratch_floats_per_warp(h->nxmod, h->nz) * sizeof(float)));

@@ -50,6 +50,55 @@ static int write_record(void* user, const mq_record* r)
     return 0;
 }
 
+/* Start model from model.dat in the working directory (aflag == 3, src/mcmc_eq.c:381,636-731): an analyse_eq result file
+ * whose STAN lines give the velocity model (depth, Vp = column 7, Vp/Vs = column 9 of the line), EQ lines the hypocentres,
+ * RES lines the station corrections and the NOISE line the eight sigmas; the letters of config line 34 (V Q R N) select
+ * which of them replace the random start values -- in every chain, as every reference process would read the same file. */
+static int apply_model_dat(const mq_config* cfg, mq_models* m, FILE* log)
+{
+    FILE* f = fopen("model.dat", "r");
+    char line[4096], tag[64];
+    const char* sw = cfg->inp_model_switch;
+    int c, k, nv = 0, nq = 0;
+    float zz[1000], vv[1000], rr[1000];
+    if (!f) { fprintf(stderr, "could not open model file\n"); return 1; }
+    while (fgets(line, sizeof line, f)) {
+        float a[16];
+        int di;
+        if (sscanf(line, "%63s", tag) != 1 || tag[0] == '#') continue;
+        if (!strcmp(tag, "STAN") && strchr(sw, 'V')) {
+            if (sscanf(line, "%*s %f %f %f %f %f %f %f %f", &a[0], &a[1], &a[2], &a[3], &a[4], &a[5], &a[6], &a[7]) < 8) continue;
+            if (nv >= m->max_dim || nv >= 1000) { fprintf(stderr, "model larger than reserved space, increase 'max # of cells/layers' in config file\n"); fclose(f); return 1; }
+            zz[nv] = a[0]; vv[nv] = a[5]; rr[nv] = a[7]; nv++;
+        } else if (!strcmp(tag, "EQ") && strchr(sw, 'Q')) {
+            if (sscanf(line, "%*s %d %f %f %f", &di, &a[0], &a[1], &a[2]) < 4 || di < 0 || di >= m->n_events) continue;
+            for (c = 0; c < m->n_chains; c++)
+                for (k = 0; k < 3; k++) m->eq[((size_t)c * m->n_events + di) * 3 + k] = a[k];
+            nq++;
+        } else if (!strcmp(tag, "RES") && strchr(sw, 'R')) {
+            if (sscanf(line, "%*s %d %f %f", &di, &a[0], &a[1]) < 3 || di < 0 || di >= m->n_stations) continue;
+            for (c = 0; c < m->n_chains; c++) { m->pres[(size_t)c * m->n_stations + di] = a[0]; m->sres[(size_t)c * m->n_stations + di] = a[1]; }
+        } else if (!strcmp(tag, "NOISE") && strchr(sw, 'N')) {
+            if (sscanf(line, "%*s %f %f %f %f %f %f %f %f", &a[0], &a[1], &a[2], &a[3], &a[4], &a[5], &a[6], &a[7]) < 8) continue;
+            for (c = 0; c < m->n_chains; c++)
+                for (k = 0; k < 4; k++) { m->noise[8 * (size_t)c + 2 * k] = a[k]; m->noise[8 * (size_t)c + 2 * k + 1] = a[4 + k]; }   /* file: p0..p3 s0..s3 */
+        }
+    }
+    fclose(f);
+    if (strchr(sw, 'V')) {
+        if (nv < 1) { fprintf(stderr, "model.dat holds no STAN line\n"); return 1; }
+        for (c = 0; c < m->n_chains; c++) {
+            m->dim[c] = nv;
+            for (k = 0; k < nv; k++) {
+                m->z[(size_t)c * m->max_dim + k] = zz[k]; m->vp[(size_t)c * m->max_dim + k] = vv[k]; m->vpvs[(size_t)c * m->max_dim + k] = rr[k];
+            }
+        }
+    }
+    if (strchr(sw, 'Q') && nq != m->n_events) { fprintf(stderr, "number of quakes does not fit pick file!\n"); return 1; }
+    if (log) fprintf(log, "start model from model.dat (%s): %d layers, %d quakes\n", sw, nv, nq);
+    return 0;
+}
+
 static unsigned long urandom_seed(void)
 {
     unsigned long v = (unsigned long)time(NULL);
@@ -76,7 +125,7 @@ static void out_name(char* dst, size_t cap, const char* pattern, int n_chains, i
 
 int main(int argc, char** argv)
 {
-    int rc = 0, n_chains = 1, device = 0, quiet = 0, i, c;
+    int rc = 0, n_chains = 1, device = 0, quiet = 0, i, c, from_file = 0;
     long seed_arg = -1;
     mq_config cfg;
     mqio_picks pk;
@@ -109,7 +158,7 @@ int main(int argc, char** argv)
     if (mqio_read_picks(argv[3], &pk) != MQ_OK) FAIL("%s", mqio_last_error());
     if (mqio_check_picks(&cfg, &pk, quiet ? NULL : stderr) != MQ_OK) FAIL("%s", mqio_last_error());
     if (cfg.tria != 0) FAIL("config line 29: only the Voronoi parameterisation (0) is implemented");
-    if (cfg.aflag == 3) FAIL("config line 34: start from model.dat (aflag 3) is not implemented");
+    if (cfg.aflag == 3) { from_file = 1; cfg.aflag = 0; }      /* src/mcmc_eq.c:381 */
 
     {
         unsigned long seed = seed_arg >= 0 ? (unsigned long)seed_arg : (cfg.true_random > 0 ? (unsigned long)cfg.true_random : urandom_seed());
@@ -136,6 +185,24 @@ int main(int argc, char** argv)
     /* start models + first forward (src/mcmc_eq.c:559-765) */
     t0 = clock();
     MQ(mq_init_chains(h));
+    if (from_file) {
+        /* the random start values stay for whatever model.dat does not supply (src/mcmc_eq.c:559-630 run before :636) */
+        mq_models m;
+        const size_t n = (size_t)n_chains, md = (size_t)(cfg.max_dim < 1000 ? cfg.max_dim : 1000), ne = (size_t)pk.view.n_events,
+                     ns = (size_t)pk.view.n_stations;
+        int bad;
+        memset(&m, 0, sizeof m);
+        m.n_chains = n_chains; m.max_dim = (int)md; m.n_events = (int)ne; m.n_stations = (int)ns;
+        m.dim = (int32_t*)calloc(n, sizeof(int32_t));
+        m.z = (float*)calloc(n * md, sizeof(float)); m.vp = (float*)calloc(n * md, sizeof(float)); m.vpvs = (float*)calloc(n * md, sizeof(float));
+        m.eq = (float*)calloc(n * ne * 3, sizeof(float)); m.pres = (float*)calloc(n * ns, sizeof(float)); m.sres = (float*)calloc(n * ns, sizeof(float));
+        m.noise = (float*)calloc(n * 8, sizeof(float)); m.origin = (float*)calloc(n * ne, sizeof(float));
+        bad = !m.dim || !m.z || !m.vp || !m.vpvs || !m.eq || !m.pres || !m.sres || !m.noise || !m.origin;
+        if (!bad) bad = mq_get_models(h, &m) != MQ_OK || apply_model_dat(&cfg, &m, quiet ? NULL : stderr) || mq_set_models(h, &m) != MQ_OK ||
+                        mq_step(h, 0, NULL) != MQ_OK;      /* a step of zero iterations scores the new start models */
+        free(m.dim); free(m.z); free(m.vp); free(m.vpvs); free(m.eq); free(m.pres); free(m.sres); free(m.noise); free(m.origin);
+        if (bad) FAIL("start from model.dat failed: %s", mq_last_error());
+    }
     MQ(mq_get_stats(h, counts, ll, rms));
     if (!quiet) {
         const long ms = (long)((clock() - t0) * 1000 / CLOCKS_PER_SEC);

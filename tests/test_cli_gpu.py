@@ -99,3 +99,75 @@ def test_out_name_without_pattern_inserts_chain_number():
     with tempfile.TemporaryDirectory() as d:
         _run(d, 2, "run.out", j_max_main=20)
         assert sorted(f for f in os.listdir(d) if f.startswith("run")) == ["run-001.out", "run-002.out"]
+
+
+def test_fw_mod_prints_what_the_reference_fw_mod_prints():
+    """host/fw_mod (C over the C ABI) against the stdout of the reference's own fw_mod for the same chain record
+    (tests/golden/fw_mod_example2.txt, written by tools/make_golden.py from oracle/_ref/fw_mod): same lines, residuals and
+    predictions within 1e-4 s, distances / depths / observed times as printed."""
+    sys_path = os.path.join(util.ROOT, "tools")
+    import sys
+    sys.path.insert(0, sys_path)
+    from make_golden import last_block
+    exe = os.path.join(util.ROOT, "mcmc_eq_b200", "host", "fw_mod")
+    assert os.path.exists(exe), "host/fw_mod not built"
+    ref = open(os.path.join(util.GOLDEN, "fw_mod_example2.txt")).read().strip().split("\n")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=77)
+        blk = os.path.join(d, "block")
+        open(blk, "w").write(last_block(open(os.path.join(util.GOLDEN, "chain_ref_example2.out")).read()))
+        r = subprocess.run([exe, cfgp, blk, pkp], cwd=d, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = r.stdout.strip().split("\n")
+    assert len(got) == len(ref) - 1 == 225 + 3600
+    worst = 0.0
+    for a, b in zip(got, ref[:-1]):
+        ta, tb = a.split(), b.split()
+        assert len(ta) == len(tb) and ta[0] == tb[0] if ta[0] == "EVENT" else ta[-1] == tb[-1]
+        if ta[0] == "EVENT":
+            assert ta[:6] == tb[:6] and abs(float(ta[6]) - float(tb[6])) < 1e-4        # origin time
+        else:
+            va, vb = [float(x) for x in ta[:6]], [float(x) for x in tb[:6]]
+            assert va[1] == vb[1] and va[2] == vb[2] and va[4] == vb[4]                 # distance, depth, observed time
+            assert abs(va[0] - vb[0]) < 1e-4 and abs(va[5] - vb[5]) < 1e-4 and abs(va[3] - vb[3]) < 1e-4
+            worst = max(worst, abs(va[5] - vb[5]))
+    # stderr: "Start model found with loglikelihood L RMS=R"
+    want = ref[-1].split()
+    have = r.stderr.strip().split("\n")[-1].split()
+    assert abs(float(have[-1].split("=")[1]) - float(want[-1].split("=")[1])) < 2e-6
+    assert float(have[-2]) == float(want[-2]) == -0.5      # the reference's constant (cal_fit_newx returns 1.0)
+
+
+def test_start_from_model_dat():
+    """aflag == 3 (config line 34): velocity model, hypocentres, station corrections and sigmas of the start model come from
+    model.dat in the working directory, an analyse_eq result file (src/mcmc_eq.c:381,636-731)."""
+    rng = np.random.default_rng(12)
+    with tempfile.TemporaryDirectory() as d:
+        zs = np.array([-1.0, 2.5, 7.0, 15.0])
+        vps = np.array([3.9, 5.1, 6.0, 6.8])
+        rs = np.array([1.9, 1.78, 1.73, 1.71])
+        eq = np.round(np.stack([rng.uniform(-8, 8, 225), rng.uniform(-8, 8, 225), rng.uniform(1, 14, 225)], 1), 3)
+        res = np.round(rng.normal(0, 0.1, (8, 2)), 3)
+        noise = np.round(rng.uniform(0.05, 0.4, 8), 3)            # file order p0 p1 p2 p3 s0 s1 s2 s3
+        with open(os.path.join(d, "model.dat"), "w") as f:
+            for z, v, r in zip(zs, vps, rs):
+                f.write("STAN %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f %7.5f\n" % (z, 9, 9, 9, 9, v, 9, r, 9, 9, 9, 0))
+            for i, q in enumerate(eq):
+                f.write("EQ %4d %9.3f %9.3f %9.3f %9.3f %9.3f %9.3f %14.3f %7.3f %7.3f %9.5f\n" % (i, q[0], q[1], q[2], 0, 0, 0, 0, 0, 0, 0))
+            for i, r in enumerate(res):
+                f.write("RES %4d %7.3f %7.3f %7.3f %7.3f\n" % (i, r[0], r[1], 0, 0))
+            f.write("NOISE " + " ".join("%7.3f" % x for x in list(noise) + [0] * 8) + "\n")
+        _run(d, 2, "rjx-%03d.out", aflag=3, inp_model_switch="VQRN", j_max_start=5, j_max_main=5, deci=5)
+        for k in (1, 2):
+            lines = open(os.path.join(d, f"rjx-{k:03d}.out")).read().split("\n")
+            sta = lines[0].split()
+            assert sta[:2] == ["sta", "ST"] and int(sta[3]) == 4
+            got_noise = np.array([float(x) for x in sta[5:13]])
+            assert np.allclose(got_noise, noise, atol=1e-6)
+            tri = np.array([float(x) for x in sta[13:13 + 12]]).reshape(4, 3)
+            assert np.allclose(tri[:, 0], zs, atol=1e-6) and np.allclose(tri[:, 1], vps, atol=1e-6) and np.allclose(tri[:, 2], rs, atol=1e-6)
+            got_eq = np.array([[float(x) for x in ln.split()[5:8]] for ln in lines[1:226]])
+            assert np.allclose(got_eq, eq, atol=1e-5)
+            got_res = np.array([[float(x) for x in ln.split()[5:7]] for ln in lines[226:234]])
+            assert np.allclose(got_res, res, atol=1e-6)
+            assert float(sta[4]) > 0

@@ -143,3 +143,22 @@ def test_host_driven_loop_with_table_backup(oracle):
     assert np.allclose(mf2[0], ref, rtol=2e-5) and np.allclose(org2[0], rorg, atol=2e-5)
     assert not np.allclose(mf2[0], mfa[0], rtol=1e-6)
     smp.close()
+
+
+def test_fine_grid_takes_the_generic_kernel(oracle):
+    """A 0.1 km grid (601 depth nodes: the plane no longer fits the fast kernel's shared memory) runs through the generic
+    one-lane-per-solve kernel with its time fields in a memory-capped global scratch; same parity bar."""
+    import mcmc_eq_b200 as mq
+    rng = np.random.default_rng(8)
+    d = tempfile.mkdtemp(prefix="mqfine_")
+    cfgp, pkp = inputs.materialise("example2", d, h=0.1, nx=481, ny=481, nz=601)
+    cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
+    assert cfg.grid.nz == 601 and abs(cfg.grid.h - 0.1) < 1e-6
+    smp = mq.Sampler(cfg, pk, 1, 0, 1)
+    st = fh.random_states(rng, cfg, pk, 1, max_layers=8)
+    mf, org = smp.forward_host(fh.fill_models(smp.new_models(32), st), 3)
+    _res, tp = smp.predictions(0)
+    ref, rorg, _r, rtp = fh.oracle_forward(cfg, pk, st[0]["z"], st[0]["vp"], st[0]["vpvs"], st[0]["eq"], st[0]["pres"], st[0]["sres"])
+    assert np.abs(tp - rtp).max() < 1e-4
+    assert np.allclose(mf[0], ref, rtol=2e-5) and np.allclose(org[0], rorg, atol=2e-5)
+    smp.close()

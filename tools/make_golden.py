@@ -187,6 +187,30 @@ def replay_ref():
     print("replay_ref:", len(log["u"]), "records,", int(log["accepted"][1:].sum()), "accepted")
 
 
+def last_block(text):
+    """The last 'mod' record of a chain file with its EQ and RES lines: the input format of fw_mod (src/fw_mod.c:412-467)."""
+    lines = text.split("\n")
+    start = max(i for i, ln in enumerate(lines) if ln.startswith("mod"))
+    out = [lines[start]]
+    for ln in lines[start + 1:]:
+        if not ln.startswith(("EQ", "RES")):
+            break
+        out.append(ln)
+    return "\n".join(out) + "\n"
+
+
+def fw_mod_ref():
+    """Per-pick predictions of the reference's own forward program for the last record of the golden chain."""
+    exe = os.path.join(util.REF_DIR, "fw_mod")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=77)
+        blk = os.path.join(d, "block")
+        open(blk, "w").write(last_block(open(os.path.join(G, "chain_ref_example2.out")).read()))
+        r = subprocess.run([exe, cfgp, blk, pkp], check=True, cwd=d, capture_output=True, text=True)
+    open(os.path.join(G, "fw_mod_example2.txt"), "w").write(r.stdout + "STDERR " + r.stderr.strip().split("\n")[-1] + "\n")
+    print("fw_mod_ref:", r.stdout.count("\n"), "lines;", r.stderr.strip().split("\n")[-1])
+
+
 if __name__ == "__main__":
     os.makedirs(G, exist_ok=True)
     inputs_of("example", os.path.join(REF, "Example/config_eqx.dat"), os.path.join(REF, "Example/picks_synth"))
@@ -195,4 +219,5 @@ if __name__ == "__main__":
     forward_ref()
     chain_ref()
     replay_ref()
+    fw_mod_ref()
     print(subprocess.run(["du", "-sh", G], capture_output=True, text=True).stdout)
