@@ -57,18 +57,6 @@ void free_view(EvalView* v)
     cudaFree(v->q_xyz); cudaFree(v->r_idx); cudaFree(v->r_d); cudaFree(v->ev_only);
 }
 
-__global__ void fill_i32(int32_t* p, size_t n, int32_t v)
-{
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-cudaError_t fill(int32_t* p, size_t n, int32_t v, cudaStream_t s)
-{
-    fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
-    count_launch();
-    return cudaGetLastError();
-}
-
 // current-state view: evaluate what is stored, write where it is stored
 __global__ void sync_cur_view(int n, const int32_t* mcur, const int32_t* tcur, const int32_t* ecur, EvalView v)
 {

@@ -11,10 +11,13 @@
 //     stencils still need (past and current time at the previous node of the walk) are carried in
 //     registers, the one node a later walk revisits (the local maximum between two minima) keeps
 //     its past value in a register.
-//   * After the box spans the full depth range the solve is a pure march over columns with a
-//     working set of ONE column per lane; receiver rows are emitted as the march passes.
+//   * After the box spans the full depth range the solve is a pure march over columns: past and
+//     current column ping-pong between two buffers, both directions of a column run as two
+//     independent chains of one lock-step loop (march_sweep3); receiver rows are emitted as the
+//     march passes.  (eik_march.cuh holds the same march with the columns in tensor memory.)
 //   * All lanes of a warp run the same instruction stream: the per-lane walk position and
-//     direction are data.  Lanes are grouped by source depth, so their boxes grow in step.
+//     direction are data.  Lanes are grouped by source depth and by the layering round the source
+//     (eikonal.cu: eik_order_tasks), so their boxes grow in step.
 //   * Head waves along a row (a faster layer on the far side, src/time_2d.c:1029-1059) are
 //     detected, not handled, by the fast sweep: the lane re-does that line with the generic
 //     sweep (eik_core.cuh) on the global-memory copy of the box that every fast sweep writes
@@ -22,7 +25,8 @@
 //     path takes the few other irregular cases (exact ties on a plateau, pre-set nodes after the
 //     minimal initialisation, boxes that touch the right edge).
 //
-// Compiles for the device and, with a 1-lane "warp", for the host (tests/emu) bit-identically.
+// Compiles for the device and, with a 1-lane "warp", for the host (tests/emu): same order, same arithmetic
+// (bit-identical to the generic core on the host; on the device the radicands' square roots are MUFU.SQRT).
 #pragma once
 #include "eik_core.cuh"
 
@@ -359,84 +363,26 @@ EIK_HD void march_sweep(bool act, const float* P, float* C, const float* S, int 
     }
 }
 
-// ---- the march, two lock-step passes -----------------------------------------------------------------------
+// ---- the march in lock-step --------------------------------------------------------------------------------------
 // Without exact ties in the past column the order in which the reference visits the nodes of a line does not
 // matter, only who is timed from whom: a node whose past time is not below its upper neighbour's is timed from
 // that neighbour (the reference reaches it walking down from a local minimum), a node not below its lower
 // neighbour's from below, a local maximum from both (the smaller wins), and a node strictly below its upper
 // neighbour and not above its lower one is where the reference's search for a local minimum stops: a root, timed
-// by 1-D transmission.  So a column is two passes, one down the column and one up, every lane at the same depth
-// at the same time, with predicated stores instead of per-lane walks: straight-line code, no votes, no state
-// machine.  The passes also see an exact tie if there is one; such a column (4 in 100 000) is re-done by
-// march_sweep, which follows the reference's order literally.
+// by 1-D transmission.  So a column is one pass down and one pass up, every lane at the same depth at the same
+// time, with predicated results instead of per-lane walks: straight-line code, no votes, no state machine.  The
+// passes also see an exact tie if there is one; such a column (4 in 100 000) is re-done by march_sweep, which
+// follows the reference's order literally.
 // P, C: indices -1 .. ke+1; P's end slots must hold kEdge (set by the caller); S[-1] = S[ke] = INF.
 constexpr float kEdge = 1.0e30f;
 
-EIK_HD bool march_sweep2(bool act, const float* P, float* C, const float* S, int ke)
-{
-    bool tie = false;
-    // ---- pass 1, k = 0 .. ke: roots and nodes timed from above (parent k-1)
-    {
-        float pprev = kEdge, pk = P[0], sprev = kInf, cn = kInf;
-#pragma unroll 4
-        for (int k = 0; k <= ke; k++) {
-            const float pnext = P[(long)(k + 1) * LS];
-            const float sk = S[(long)k * LS];
-            const float dt = pk - pprev;
-            const bool up = dt >= 0.f;                       // timed from node k-1
-            const bool root = !up && (pnext >= pk);          // the search for a local minimum stops here
-            tie = tie || (dt == 0.f);
-            const float lim = sprev * kRsqrt2;
-            const float s0sq = sprev * sprev;
-            float est = pk + sqrt_pos(fmaf(-dt, dt, s0sq));
-            float cv = (dt < lim) ? est : kInf;
-            const float dt2 = cn - pprev;
-            est = cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
-            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
-            cv = fminf(cv, pk + sk);
-            cv = fminf(cv, fmaf(sprev, kSqrt2, pprev));
-            const float cmin = fminf(kInf, pk + eik::fmin_ref(sprev, sk));
-            const float val = up ? cv : (root ? cmin : kInf);
-            C[(long)k * LS] = val;
-            cn = val; pprev = pk; pk = pnext; sprev = sk;
-        }
-    }
-    // ---- pass 2, k = ke-1 .. 0: nodes timed from below (parent k+1); a local maximum keeps the smaller value
-    {
-        float pnx = P[(long)ke * LS], cn = C[(long)ke * LS];
-#pragma unroll 4
-        for (int k = ke - 1; k >= 0; k--) {
-            const float pk = P[(long)k * LS];
-            const float s0 = S[(long)k * LS];
-            const float hs1 = S[(long)(k - 1) * LS];
-            const float cold = C[(long)k * LS];
-            const float dt = pk - pnx;
-            const bool down = dt >= 0.f;
-            tie = tie || (dt == 0.f);
-            const float lim = s0 * kRsqrt2;
-            const float s0sq = s0 * s0;
-            float est = pk + sqrt_pos(fmaf(-dt, dt, s0sq));
-            float cv = fminf(cold, (dt < lim) ? est : kInf);
-            const float dt2 = cn - pnx;
-            est = cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
-            cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
-            cv = fminf(cv, pk + hs1);
-            cv = fminf(cv, fmaf(s0, kSqrt2, pnx));
-            const float val = down ? cv : cold;
-            if (down) C[(long)k * LS] = val;
-            cn = val; pnx = pk;
-        }
-    }
-    return act && tie;
-}
-
 // ---- the march, both passes in one loop -----------------------------------------------------------------------
-// The two passes of march_sweep2 never feed each other: a node timed from above cannot have a neighbour above it
+// The two passes never feed each other: a node timed from above cannot have a neighbour above it
 // that is timed from below unless the two past times are equal (a tie, handled elsewhere), and a root's value only
 // depends on the past column.  So the downward chain (A, k = i) and the upward chain (B, k = ke - i) run in the same
 // loop iteration as two independent dependency chains -- twice the instruction-level parallelism per warp, which is
 // what a kernel limited to ~2 warps per scheduler by its shared-memory footprint needs -- and meet in the middle;
-// whoever reaches a node second merges with fminf.  Same values as march_sweep2, bit for bit.
+// whoever reaches a node second merges with fminf.
 // One node of each chain.  A: node k timed from k-1 (state: past times of k-1 and k, cell k-1, current time of k-1);
 // B: node k timed from k+1.  Both also time the roots they pass (1-D transmission) so that neither waits for the other.
 struct ChainA { float pprev, pk, sprev, cn; };
