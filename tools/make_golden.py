@@ -211,6 +211,63 @@ def fw_mod_ref():
     print("fw_mod_ref:", r.stdout.count("\n"), "lines;", r.stderr.strip().split("\n")[-1])
 
 
+def parse_chain(text, n_events):
+    """Trajectory of one chain file: per 'mod' record rms, dimension, sigmas, mean hypocentre depth, rms of the station
+    corrections; and the a/r counters."""
+    import re
+    recs, cur = [], None
+    for ln in text.split("\n"):
+        t = ln.split()
+        if not t:
+            continue
+        if t[0] == "mod":
+            cur = dict(number=int(t[2]), dim=int(t[3]), rms=float(t[4]), noise=[float(x) for x in t[5:13]], z=[], res=[],
+                       vp=[float(x) for x in t[14::3][:int(t[3])]])
+            recs.append(cur)
+        elif t[0] == "EQ" and cur is not None and t[1] not in ("ST", "BF"):
+            cur["z"].append(float(t[7]))
+        elif t[0] == "RES" and cur is not None and t[1] not in ("ST", "BF"):
+            cur["res"].append((float(t[5]), float(t[6])))
+        elif t[0] in ("bat", "sta"):
+            cur = None
+    cnt = {m.group(1).strip(): (int(m.group(2)), int(m.group(3))) for m in re.finditer(r"cnt (\S+)\s+a/r\s+(\d+)\s+(\d+)", text)}
+    tested = int(re.search(r"cnt RMS tested\s+(\d+)", text).group(1))
+    return dict(number=np.array([r["number"] for r in recs]), dim=np.array([r["dim"] for r in recs]),
+                rms=np.array([r["rms"] for r in recs]), noise=np.array([r["noise"] for r in recs]),
+                zmean=np.array([np.mean(r["z"]) for r in recs]), res_rms=np.array([np.sqrt(np.mean(np.square(r["res"]))) for r in recs]),
+                vp_mean=np.array([np.mean(r["vp"]) for r in recs]),
+                acc=np.array([cnt[k][0] for k in ("noise", "P-vel", "Vp/Vs", "quake", "resid", "move", "birth", "death")]),
+                rej=np.array([cnt[k][1] for k in ("noise", "P-vel", "Vp/Vs", "quake", "resid", "move", "birth", "death")]), tested=tested)
+
+
+ENSEMBLE = dict(j_max_start=1500, j_max_main=2500, deci=100)
+
+
+def ensemble_ref(n_chains=32):
+    """Ensemble statistics of independent reference chains (Example2, 4000 accepted models each, seeds 100..): the
+    posterior-level fixture.  Free-running chains of another RNG cannot match these sample by sample, but their ensemble must
+    be statistically indistinguishable (tests/test_ensemble_gpu.py)."""
+    exe = os.path.join(util.REF_DIR, "mcmc_eq")
+    out = []
+    with tempfile.TemporaryDirectory() as d:
+        procs = []
+        for k in range(n_chains):
+            cfgp, pkp = inputs.materialise("example2", os.path.join(d, f"c{k}"), true_random=100 + k, **ENSEMBLE)
+            procs.append((k, subprocess.Popen([exe, cfgp, os.path.join(d, f"rjx-{k:03d}.out"), pkp], cwd=os.path.join(d, f"c{k}"),
+                                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)))
+            if len(procs) == (os.cpu_count() or 4):
+                for _k, p in procs:
+                    p.wait()
+                procs = []
+        for _k, p in procs:
+            p.wait()
+        for k in range(n_chains):
+            out.append(parse_chain(open(os.path.join(d, f"rjx-{k:03d}.out")).read(), 225))
+    keys = out[0].keys()
+    np.savez_compressed(os.path.join(G, "ensemble_ref_example2.npz"), **{k: np.stack([np.asarray(o[k]) for o in out]) for k in keys})
+    print("ensemble_ref:", n_chains, "chains; final rms", np.mean([o["rms"][-1] for o in out]), "+-", np.std([o["rms"][-1] for o in out]))
+
+
 if __name__ == "__main__":
     os.makedirs(G, exist_ok=True)
     inputs_of("example", os.path.join(REF, "Example/config_eqx.dat"), os.path.join(REF, "Example/picks_synth"))
@@ -220,4 +277,5 @@ if __name__ == "__main__":
     chain_ref()
     replay_ref()
     fw_mod_ref()
+    ensemble_ref()
     print(subprocess.run(["du", "-sh", G], capture_output=True, text=True).stdout)
