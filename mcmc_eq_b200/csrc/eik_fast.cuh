@@ -464,16 +464,30 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
 }
 
 // ---- perimeter <-> global window -------------------------------------------------------------------
+// n elements from src (element stride ss) to dst (element stride ds), eight loads in flight before the first store:
+// the copies between the global window and shared memory are latency-bound one-lane-wide loops otherwise.
+EIK_HD void copy_strided(float* dst, long ds, const float* src, long ss, int n)
+{
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = src[(long)(i + u) * ss];
+#pragma unroll
+        for (int u = 0; u < 8; u++) dst[(long)(i + u) * ds] = v[u];
+    }
+    for (; i < n; i++) dst[(long)i * ds] = src[(long)i * ss];
+}
+
 template <class G>
 EIK_HD void load_perimeter(const G& g, const Lane& L, int row_len)
 {
     // a row is only kept while the box can still grow on that side; the two rows share one buffer
     // (top from the front, bottom from the back) whose length covers them exactly under that rule
-    for (int x = 0; x <= g.X1; x++) {
-        if (g.Y0 > 0) L.ROW[(size_t)x * LS] = g.T(x, g.Y0);
-        if (g.Y1 < g.my) L.ROW[(size_t)(row_len - 1 - x) * LS] = g.T(x, g.Y1);
-    }
-    for (int y = g.Y0; y <= g.Y1; y++) L.COL[(size_t)y * LS] = g.T(g.X1, y);
+    const long xs = (long)g.ny * g.ts;   // node (x,y) of the window lives at t[(x*ny + y)*ts]
+    if (g.Y0 > 0) copy_strided(L.ROW, LS, &g.T(0, g.Y0), xs, g.X1 + 1);
+    if (g.Y1 < g.my) copy_strided(L.ROW + (size_t)(row_len - 1) * LS, -LS, &g.T(0, g.Y1), xs, g.X1 + 1);
+    copy_strided(L.COL + (size_t)g.Y0 * LS, LS, &g.T(g.X1, g.Y0), g.ts, g.Y1 - g.Y0 + 1);
 }
 
 template <class Medium>
@@ -734,8 +748,8 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
         if (bf.active) {
             // every second fine node is a coarse node (src/time_2d.c:887-890); the fine field is complete in WF
             for (int i = 0, ii = 0; ii < bf.nx; ii += 2, i++)
-                for (int j = j0 + hy, jj = hy; jj < bf.ny; jj += 2, j++)
-                    L.W[((size_t)i * nz + j) * LS] = L.WF[((size_t)ii * bf.ny + jj) * LS];
+                copy_strided(L.W + ((size_t)i * nz + j0 + hy) * LS, LS, L.WF + ((size_t)ii * bf.ny + hy) * LS, 2 * LS,
+                             (bf.ny - hy + 1) / 2);
             bc.X1 = (kInitMin < mx) ? kInitMin : mx;
             bc.Y0 = (t.iz - kInitMin > 0) ? t.iz - kInitMin : 0;
             bc.Y1 = (t.iz + kInitMin < my) ? t.iz + kInitMin : my;
@@ -759,7 +773,7 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     if (t.valid && !whole) {
         if (t.out)
             for (int r = 0; r < n_rows; r++)
-                for (int x = 0; x <= xbox_end; x++) t.out[(long)r * t.out_rstride + x] = L.W[((size_t)x * nz + rows[r]) * LS];
+                copy_strided(t.out + (long)r * t.out_rstride, 1, L.W + (size_t)rows[r] * LS, (long)nz * LS, xbox_end + 1);
         if (t.full)
             for (int x = 0; x <= xbox_end; x++)
                 for (int y = 0; y < nz; y++) t.full[(size_t)x * nz + y] = L.W[((size_t)x * nz + y) * LS];
