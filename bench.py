@@ -328,7 +328,9 @@ def main():
     alg_bytes_per_solve = 4 * nz + 4 * nxmod * nz            # read nz slownesses, write the field
     peak, peak_src = measured_peak()
     roofline = None
-    if eik_n > 0:
+    # the roofline figure needs the exact number of solves per launch: only a pure 'P' string rebuilds both tables of every
+    # chain in every step (V rebuilds one, B/D/M can be ineligible, Q/R/N rebuild none)
+    if eik_n > 0 and set(args.proposals) <= {"P"}:
         t_launch = eik_ms / eik_n / 1000.0
         achieved = alg_bytes_per_solve * solves_per_launch / t_launch / 1e9
         smem_alg = 32.0 * nxmod * nz * solves_per_launch / t_launch / 1e9
