@@ -1,9 +1,13 @@
-/* fw_mod_main.c -- the reference's forward program `fw_mod` on top of the B200 library (plain C over the C ABI).
+/* fw_mod_main.c -- the reference's forward programs `fw_mod` and `fw` on top of the B200 library (plain C over the C ABI).
  *
  *     fw_mod <config_eqx.dat> <model_block> <picks> [-d device]
+ *     fw     <config.dat>     <res.dat>     <picks> [-d device]        (this file compiled with -DFW_GRIDDED)
  *
- * Arguments as the reference's (src/fw_mod.c).  <model_block> is one record cut from a chain file: the "mod ..." line
- * (src/fw_mod.c:421-445), then one "EQ ..." line per event (:450-457) and one "RES ..." line per station (:460-464).
+ * Arguments as the reference's.  fw_mod (src/fw_mod.c): <model_block> is one record cut from a chain file: the "mod ..."
+ * line (src/fw_mod.c:421-445), then one "EQ ..." line per event (:450-457) and one "RES ..." line per station (:460-464).
+ * fw (src/fw.c:405-455): <res.dat> is an analyse_eq result file: nz "STAN" lines (depth, ..., Vp = 7th and Vp/Vs = 9th
+ * token) that become nz nuclei, one "EQ" line per event, as many "EZ" lines (skipped), one "RES" line per station in
+ * station order, one noise line -- what Example/make_synthetics and scriptsV2/mkSynthetics.sh build to make synthetic picks.
  * Output as cal_fit_newx prints it with out == 1 (src/misfit.c:130-143): per event
  *     EVENT i  reftime x y z origin
  * and per pick (P first, then S, file order)
@@ -57,6 +61,35 @@ int main(int argc, char** argv)
     resid = (float*)calloc((size_t)np, sizeof(float)); tpred = (float*)calloc((size_t)np, sizeof(float));
     if (!buf || !z || !vp || !vpvs || !eq || !origin || !pres || !sres || !resid || !tpred) FAIL("out of memory");
     if (!fgets(buf, (int)cap, f)) FAIL("empty model file %s", argv[2]);
+#ifdef FW_GRIDDED
+    {   /* src/fw.c:405-455 */
+        int k;
+        char a[64];
+        float t[11];
+        dim = cfg.grid.nz;
+        if (dim > 1000) FAIL("nz %d > 1000 nuclei", dim);
+        for (k = 0; k < 8; k++) noise[k] = cfg.start_noise > 0.f ? cfg.start_noise : 1.f;
+        for (k = 0; k < dim; k++) {
+            if (k > 0 && !fgets(buf, (int)cap, f)) FAIL("model file: STAN line %d missing", k);
+            if (sscanf(buf, "%63s %f %f %f %f %f %f %f %f", a, &t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7]) < 9)
+                FAIL("model file: STAN line %d short", k);
+            z[k] = t[0]; vp[k] = t[5]; vpvs[k] = t[7];
+        }
+        for (i = 0; i < ne; i++) {   /* "EQ i x y z . . . . origin ." */
+            int di;
+            if (!fgets(buf, (int)cap, f) || sscanf(buf, "%63s %d %f %f %f %f %f %f %f %f", a, &di, &eq[3 * i], &eq[3 * i + 1], &eq[3 * i + 2],
+                                                    &t[0], &t[1], &t[2], &t[3], &origin[i]) < 5)
+                FAIL("model file: EQ line %d missing or short", i);
+        }
+        for (i = 0; i < ne; i++)
+            if (!fgets(buf, (int)cap, f)) FAIL("model file: EZ line %d missing", i);
+        for (i = 0; i < ns; i++) {   /* "RES i pres sres . ." -- by line order, like the reference */
+            int di;
+            if (!fgets(buf, (int)cap, f) || sscanf(buf, "%63s %d %f %f", a, &di, &pres[i], &sres[i]) < 4)
+                FAIL("model file: RES line %d missing or short", i);
+        }
+    }
+#else
     {   /* "mod XX number dim rms p0 p1 p2 p3 s0 s1 s2 s3 z vp vpvs ..." (src/fw_mod.c:421-445) */
         char* tok = strtok(buf, " ");
         float pn[8];
@@ -90,6 +123,8 @@ int main(int argc, char** argv)
             FAIL("model file: RES line %d missing or short", i);
     }
 
+#endif
+    if (cfg.max_dim < dim) cfg.max_dim = dim;      /* the reference's forward programs do not look at line 8 */
     MQ(mq_create(&cfg, &pk.view, 1, device, 1, &h));
     dim32 = dim;
     m.n_chains = 1; m.max_dim = dim; m.n_events = ne; m.n_stations = ns;

@@ -171,3 +171,25 @@ def test_start_from_model_dat():
             got_res = np.array([[float(x) for x in ln.split()[5:7]] for ln in lines[226:234]])
             assert np.allclose(got_res, res, atol=1e-6)
             assert float(sta[4]) > 0
+
+
+def test_fw_prints_what_the_reference_fw_prints():
+    """host/fw (gridded model from an analyse_eq-style result file, src/fw.c) against the reference fw's own output for the
+    same res.dat (tests/golden/fw_example2.npz, from oracle/_ref/fw): what Example/make_synthetics turns into synthetic picks."""
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "tools"))
+    from make_golden import write_res_dat, parse_forward_stdout
+    exe = os.path.join(util.ROOT, "mcmc_eq_b200", "host", "fw")
+    assert os.path.exists(exe), "host/fw not built"
+    g = np.load(os.path.join(util.GOLDEN, "fw_example2.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d)
+        res = os.path.join(d, "res.dat")
+        write_res_dat(res, g["zn"], g["vpn"], g["rn"], g["eq"], g["pres"], g["sres"])
+        r = subprocess.run([exe, cfgp, res, pkp], cwd=d, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    ev, pk = parse_forward_stdout(r.stdout)
+    assert ev.shape == g["events"].shape and pk.shape == g["picks"].shape
+    assert np.array_equal(ev[:, :4], g["events"][:, :4]) and np.abs(ev[:, 4] - g["events"][:, 4]).max() < 1e-4   # origin times
+    assert np.array_equal(pk[:, [1, 2, 4, 6]], g["picks"][:, [1, 2, 4, 6]])      # distance, depth, observed time, phase
+    assert np.abs(pk[:, [0, 3, 5]] - g["picks"][:, [0, 3, 5]]).max() < 1e-4      # residual, origin, predicted time

@@ -240,6 +240,52 @@ def parse_chain(text, n_events):
                 rej=np.array([cnt[k][1] for k in ("noise", "P-vel", "Vp/Vs", "quake", "resid", "move", "birth", "death")]), tested=tested)
 
 
+def write_res_dat(path, zn, vpn, rn, eq, pres, sres):
+    """An analyse_eq-style result file the way Example/make_synthetics builds it for fw (src/fw.c:405-455)."""
+    with open(path, "w") as f:
+        for z, v, r in zip(zn, vpn, rn):
+            f.write("STAN %g %g 0 %g 0 %g 0 %g 0 %g %g 0.01\n" % (z, v, r, v, r, v, r))
+        for tag in ("EQ", "EZ"):
+            for i, q in enumerate(eq):
+                f.write("%s %d %g %g %g 0 0 0 0 0 0 0\n" % (tag, i, q[0], q[1], q[2]))
+        for i in range(len(pres)):
+            f.write("RES %d %g %g 0 0\n" % (i, pres[i], sres[i]))
+        f.write("NOISE " + " ".join(["0.1"] * 16) + "\n")
+
+
+def parse_forward_stdout(text):
+    ev, pk = [], []
+    for ln in text.strip().split("\n"):
+        t = ln.split()
+        if t[0] == "EVENT":
+            ev.append([float(x) for x in t[2:7]])
+        else:
+            pk.append([float(x) for x in t[:6]] + [1.0 if t[6] == "S" else 0.0])
+    return np.array(ev), np.array(pk)
+
+
+def fw_ref():
+    """Predictions of the reference's fw for a gridded model (61 depth nodes) on the Example2 picks."""
+    exe = os.path.join(util.REF_DIR, "fw")
+    rng = np.random.default_rng(77)
+    cfgd, arr = inputs.load("example2")
+    nz, h, z0 = cfgd["nz"], cfgd["h"], cfgd["z0"]
+    zn = z0 + h * np.arange(nz)
+    vpn = np.round(3.5 + 0.25 * np.maximum(zn, 0) + np.where(zn > 8, 0.6, 0.0) + np.where(zn > 17, 0.5, 0.0), 3)
+    rn = np.round(1.9 - 0.01 * np.maximum(zn, 0), 3)
+    ne, ns = len(arr["n_p"]), int(arr["st_id"].max()) + 1
+    eq = np.round(np.stack([rng.uniform(-8, 8, ne), rng.uniform(-8, 8, ne), rng.uniform(1, 14, ne)], 1), 3)
+    pres, sres = np.round(rng.normal(0, 0.1, ns), 3), np.round(rng.normal(0, 0.15, ns), 3)
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d)
+        res = os.path.join(d, "res.dat")
+        write_res_dat(res, zn, vpn, rn, eq, pres, sres)
+        r = subprocess.run([exe, cfgp, res, pkp], check=True, cwd=d, capture_output=True, text=True)
+    ev, pk = parse_forward_stdout(r.stdout)
+    np.savez_compressed(os.path.join(G, "fw_example2.npz"), zn=zn, vpn=vpn, rn=rn, eq=eq, pres=pres, sres=sres, events=ev, picks=pk)
+    print("fw_ref:", ev.shape, pk.shape, r.stderr.strip().split("\n")[-1])
+
+
 ENSEMBLE = dict(j_max_start=1500, j_max_main=2500, deci=100)
 
 
@@ -277,5 +323,6 @@ if __name__ == "__main__":
     chain_ref()
     replay_ref()
     fw_mod_ref()
+    fw_ref()
     ensemble_ref()
     print(subprocess.run(["du", "-sh", G], capture_output=True, text=True).stdout)
