@@ -82,17 +82,24 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ float sentinel(int k, int ke) { return k < 0 ? kEdge : kEdge * (1.0f + (float)(k - ke) * (1.0f / 1024.0f)); }
 
 // One column: past column in TMEM array tp, new column into array tc (column addresses of this warp's lane quarter).
-// S: this lane's slowness cells in shared memory, cell k at S[k*32], S[-2..-1] = S[ke..] = INF.
+// Slowness cells: either in shared memory (S: cell k at S[k*32], S[-2..-1] = S[ke..] = INF) or, with S_TMEM, in a third
+// TMEM array tS (cell k at column k+1, cells -1 and ke.. = INF).
 // MASKED: lanes with need == false keep their past column (their box phase ended at a later column than the others').
-template <int NB, bool MASKED>
-__device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, const float* S)
+template <int NB, bool MASKED, bool S_TMEM>
+__device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, const float* S, uint32_t tS)
 {
     constexpr int CA = 4 * NB;
     bool tie = false;
-    float pa_cur[4], pb_cur[4];
+    float pa_cur[4], pb_cur[4], sa_cur[4], sb_cur[4];
     tmem_ld4(tp, pa_cur);
     tmem_ld4(tp + 4 * (NB - 1), pb_cur);
+    if (S_TMEM) { tmem_ld4(tS, sa_cur); tmem_ld4(tS + 4 * (NB - 1), sb_cur); }
+    else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) { sa_cur[c] = 0.f; sb_cur[c] = 0.f; }
+    }
     tmem_wait_ld(pa_cur, pb_cur);
+    tmem_wait_ld(sa_cur, sb_cur);
     // chain A starts at node -1 (parent -2: nothing there), chain B at node CA-2 (parent CA-1: nothing there)
     eikf::ChainA a{2.0f * kEdge, pa_cur[0], kInf, kInf};
     eikf::ChainB b{4.0f * kEdge, pb_cur[3], kInf, kInf};
@@ -102,12 +109,18 @@ __device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, 
 #pragma unroll 1
     for (int j = 0; j < NB; j++) {
         const bool second = j >= NB / 2;         // the other chain has been at these nodes
-        float pa_nxt[4], pb_nxt[4], ca_old[4], cb_old[4];
+        float pa_nxt[4], pb_nxt[4], ca_old[4], cb_old[4], sa_nxt[4], sb_nxt[4];
         if (j == NB / 2) tmem_wait_st();         // its stores must have landed before they are read back
-        if (j + 1 < NB) { tmem_ld4(tp + 4 * (j + 1), pa_nxt); tmem_ld4(tp + 4 * (NB - 2 - j), pb_nxt); }
-        else {
+        if (j + 1 < NB) {
+            tmem_ld4(tp + 4 * (j + 1), pa_nxt); tmem_ld4(tp + 4 * (NB - 2 - j), pb_nxt);
+            if (S_TMEM) { tmem_ld4(tS + 4 * (j + 1), sa_nxt); tmem_ld4(tS + 4 * (NB - 2 - j), sb_nxt); }
+        } else {
 #pragma unroll
-            for (int c = 0; c < 4; c++) { pa_nxt[c] = 4.0f * kEdge; pb_nxt[c] = 2.0f * kEdge; }
+            for (int c = 0; c < 4; c++) { pa_nxt[c] = 4.0f * kEdge; pb_nxt[c] = 2.0f * kEdge; sa_nxt[c] = kInf; sb_nxt[c] = kInf; }
+        }
+        if (!S_TMEM || j + 1 >= NB) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) { if (!S_TMEM) { sa_nxt[c] = 0.f; sb_nxt[c] = 0.f; } }
         }
         if (second) { tmem_ld4(tc + 4 * j, ca_old); tmem_ld4(tc + 4 * (NB - 1 - j), cb_old); }
         else {
@@ -116,18 +129,22 @@ __device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, 
         }
         tmem_wait_ld(pa_nxt, pb_nxt);
         tmem_wait_ld(ca_old, cb_old);
+        if (S_TMEM) tmem_wait_ld(sa_nxt, sb_nxt);
         float va[4], vb[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            // chain A at node 4j-1+c
+            // chain A at node 4j-1+c: S[ka] is column 4j+c of the S array = element c of group j
             const float own_a = a.pk;
-            float v = eikf::chain_a_node(a, (c < 3) ? pa_cur[c + 1] : pa_nxt[0], sa[0], tie);
+            const float sk = S_TMEM ? sa_cur[c] : sa[0];
+            float v = eikf::chain_a_node(a, (c < 3) ? pa_cur[c + 1] : pa_nxt[0], sk, tie);
             v = fminf(v, ca_old[c]);
             va[c] = (MASKED && !need) ? own_a : v;
             sa += 32;
-            // chain B at node CA-2-4j-c
+            // chain B at node kb = CA-2-4j-c: S[kb-1] is column kb of the S array = element 2-c of group NB-1-j (c < 3),
+            // element 3 of the next lower group (c == 3)
             const float own_b = b.pk;
-            float w = eikf::chain_b_node(b, (c < 3) ? pb_cur[2 - c] : pb_nxt[3], sb[0]);
+            const float hs1 = S_TMEM ? ((c < 3) ? sb_cur[2 - c] : sb_nxt[3]) : sb[0];
+            float w = eikf::chain_b_node(b, (c < 3) ? pb_cur[2 - c] : pb_nxt[3], hs1);
             w = fminf(w, cb_old[3 - c]);
             vb[3 - c] = (MASKED && !need) ? own_b : w;
             sb -= 32;
@@ -135,7 +152,7 @@ __device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, 
         tmem_st4(tc + 4 * j, va);
         tmem_st4(tc + 4 * (NB - 1 - j), vb);
 #pragma unroll
-        for (int c = 0; c < 4; c++) { pa_cur[c] = pa_nxt[c]; pb_cur[c] = pb_nxt[c]; }
+        for (int c = 0; c < 4; c++) { pa_cur[c] = pa_nxt[c]; pb_cur[c] = pb_nxt[c]; sa_cur[c] = sa_nxt[c]; sb_cur[c] = sb_nxt[c]; }
     }
     return need && tie;
 }

@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims 
 // What a solve does before its march is decided by the layering round its source: the half-width of the
 // quasi-homogeneous box (distance to the nearest interface above and below, src/time_2d.c:598-644) selects the kind
 // of initialisation and the size of the seed box, the next interfaces decide when rows start to carry head waves.
-// Key = source depth (major, so that the lanes of a warp share the box schedule), then those distances.
+// Key = source depth (major, so that the lanes of a warp share the box schedule; in ascending order: measured better than edges-first or middle-first), then
+// those distances.
 __global__ void eik_key_kernel(EikBatch b, int max_solves, uint64_t* keys, int32_t* vals)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(128) eik_march_kernel(EikBatch b)
         const int xhi = __reduce_max_sync(0xffffffffu, live ? x1 : -1);
         for (int line = xlo + 1; line <= mx; line++) {
             const bool need = live && line > x1;
-            const bool tie = (line <= xhi) ? eikm::tmem_sweep<NB, true>(need, tp, tc, S) : eikm::tmem_sweep<NB, false>(need, tp, tc, S);
+            const bool tie = (line <= xhi) ? eikm::tmem_sweep<NB, true, false>(need, tp, tc, S, 0u) : eikm::tmem_sweep<NB, false, false>(need, tp, tc, S, 0u);
             eikm::tmem_wait_st();
             if (__any_sync(0xffffffffu, tie)) {
                 // an exact tie in the past column: follow the reference's order literally (march_sweep) on a shared-memory copy
@@ -325,6 +326,243 @@ __global__ void __launch_bounds__(128) eik_march_kernel(EikBatch b)
     if (warp == 0) eikm::tmem_dealloc<COLS>(s_tmem);
 }
 
+// ---- the pipelined kernel: box phase in shared memory, march in tensor memory, in ONE persistent CTA per SM --------------
+// The fused kernel holds 9 warps per SM because every warp keeps 24.7 KB of shared memory for its whole life, although it
+// only needs it for the box phase (per-lane indices); the march (warp-uniform indices) can live in TMEM.  Here 16 warps
+// per SM share kSlices shared-memory slices and 8 TMEM sets (past column, current column, slowness column = 3 x 64
+// columns; two sets per lane quarter): a warp takes a slice for the box phase of a task, moves the task's last column and
+// slowness column into a TMEM set, gives the slice back and marches in tensor memory.  At any time about half of the warps
+// are in the latency-bound box phase and half in the issue-bound march, and there are 16 of them instead of 9.
+// Resources are taken in a fixed order (slice, then TMEM set; the tie scratch last and never while waiting for anything
+// else), holders of a TMEM set never wait for a slice: no cycle, no deadlock.
+constexpr int kPipeWarps = 16;
+constexpr int kPipeCA = 64;          // nodes -1 .. 62 per TMEM column array: nz <= 62
+constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time columns + slowness column of the tie scratch
+
+struct PipeCtl {
+    uint32_t tmem;                   // base address of the CTA's 512 TMEM columns
+    unsigned slice_free;             // bit i: shared-memory slice i is free
+    unsigned tset_free[4];           // per lane quarter: bit i: TMEM set i is free
+    int tie_lock;
+};
+
+__device__ __forceinline__ int pipe_acquire(unsigned* mask, int lane)
+{
+    int got = -1;
+    if (lane == 0) {
+        for (;;) {
+            const unsigned m = *(volatile unsigned*)mask;
+            if (m) {
+                const int bit = __ffs(m) - 1;
+                if (atomicAnd(mask, ~(1u << bit)) & (1u << bit)) { got = bit; break; }
+            } else {
+                __nanosleep(100);
+            }
+        }
+        __threadfence_block();
+    }
+    return __shfl_sync(0xffffffffu, got, 0);
+}
+__device__ __forceinline__ void pipe_release(unsigned* mask, int bit, int lane)
+{
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicOr(mask, 1u << bit); }
+}
+
+__global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b, eikf::Dims D, int n_slices, int* task_counter)
+{
+    constexpr int CA = kPipeCA, NB = CA / 4;
+    extern __shared__ float smem_p[];
+    __shared__ PipeCtl ctl;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = warp & 3;
+    if (warp == 0) eikm::tmem_alloc<512>(&ctl.tmem);
+    if (threadIdx.x == 0) {
+        ctl.slice_free = (1u << n_slices) - 1u;
+        for (int q = 0; q < 4; q++) ctl.tset_free[q] = 3u;
+        ctl.tie_lock = 0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const size_t slice_floats = (size_t)eikf::smem_floats_per_lane(D) * 32;
+    // scratch of the literal walk for a column with an exact tie (4 in 100 000): global memory, one per CTA, under a lock
+    float* tieP = b.tie_scratch + (size_t)blockIdx.x * kPipeTieFloats + 32 + lane;   // node k at tieP[k*32], k = -1 .. CA-2
+    float* tieC = tieP + (size_t)CA * 32;
+    float* tieS = tieC + (size_t)CA * 32 + 32;                             // cell k at tieS[k*32], k = -2 .. CA-1
+    // slowness column of the third TMEM set of each lane quarter (unused: two sets per quarter)
+    float* S3 = nullptr;
+    const int nz = b.nz, ke = nz - 1, mx = b.nxmod - 1, nodes = b.nxmod * b.nz;
+    const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
+    const int n_solves = n_items * nz;
+    const int n_tasks = (n_solves + 31) >> 5;
+    const size_t wfloats = ((size_t)D.wx * D.nz + kFineNodes) * 32;
+    float* Wbase = b.scratch + (size_t)(blockIdx.x * kPipeWarps + warp) * wfloats + lane;
+    (void)nodes;
+
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= n_tasks) break;
+        int g = task * 32 + lane;
+        if (b.order) g = b.order[g];
+        // ---- box phase on a shared-memory slice
+        const int sl = pipe_acquire(&ctl.slice_free, lane);
+        eikf::Lane L;
+        eikf::carve_shared(smem_p + (size_t)sl * slice_floats + lane, D, &L);
+        L.W = Wbase;
+        L.WF = L.W + (size_t)D.wx * D.nz * 32;
+        eikf::LaneTask t;
+        t.valid = g >= 0 && g < n_solves;
+        t.iz = 0; t.slow = nullptr; t.out = nullptr; t.out_rstride = 0; t.full = nullptr;
+        int x1 = -1;
+        t.hand_col = L.COL;          // the last column of the box phase already sits there
+        t.hand_x1 = &x1;
+        if (t.valid) {
+            t.iz = g / n_items;
+            const int item = g - t.iz * n_items;
+            t.slow = b.slow + (size_t)item * nz;
+            float* tab = b.row_out ? b.row_out[item] : b.row_out_base + (size_t)item * b.row_item_stride;
+            t.out = tab + (size_t)t.iz * b.xpitch;
+            t.out_rstride = (long)nz * b.xpitch;
+        }
+        const int rc = eikf::solve_warp(D, L, t, b.rows, b.n_rows);
+        if (t.valid && b.status_min && rc < 0) atomicMin(b.status_min, rc);
+        const bool live = x1 >= 0 && x1 < mx;
+        if (!__any_sync(0xffffffffu, live)) { pipe_release(&ctl.slice_free, sl, lane); continue; }
+        // ---- move the task into a TMEM set of this warp's lane quarter, give the slice back
+        const int ts = pipe_acquire(&ctl.tset_free[quarter], lane);
+        // sets 0 and 1: columns [0,192) and [192,384) = past | current | slowness; set 2: columns [384,512) = past | current
+        const bool s_tmem = ts < 2;
+        const uint32_t tset = ctl.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ts * 3 * CA);
+        const uint32_t tS = tset + 2 * CA;
+        for (int q = 0; q < NB; q++) {
+            float v[4], w[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int k = 4 * q - 1 + c;
+                v[c] = (k >= 0 && k <= ke) ? (live ? L.COL[(size_t)k * 32] : 0.f) : eikm::sentinel(k, ke);
+                w[c] = (live && k >= 0 && k < ke) ? L.S[(size_t)k * 32] : kInfM;
+            }
+            eikm::tmem_st4(tset + 4 * q, v);
+            if (s_tmem) eikm::tmem_st4(tS + 4 * q, w);
+            else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) S3[(long)(4 * q - 1 + c) * 32] = w[c];
+            }
+        }
+        if (!s_tmem) { S3[-64] = kInfM; S3[(long)(CA - 1) * 32] = kInfM; }   // (not reached: two sets per quarter)
+        eikm::tmem_wait_st();
+        pipe_release(&ctl.slice_free, sl, lane);
+        // ---- march in tensor memory
+        uint32_t tp = tset, tc = tset + CA;
+        const int xlo = __reduce_min_sync(0xffffffffu, live ? x1 : 0x7fffffff);
+        const int xhi = __reduce_max_sync(0xffffffffu, live ? x1 : -1);
+        for (int line = xlo + 1; line <= mx; line++) {
+            const bool need = live && line > x1;
+            bool tie;
+            if (s_tmem) tie = (line <= xhi) ? eikm::tmem_sweep<NB, true, true>(need, tp, tc, nullptr, tS)
+                                            : eikm::tmem_sweep<NB, false, true>(need, tp, tc, nullptr, tS);
+            else tie = (line <= xhi) ? eikm::tmem_sweep<NB, true, false>(need, tp, tc, S3, 0u)
+                                     : eikm::tmem_sweep<NB, false, false>(need, tp, tc, S3, 0u);
+            eikm::tmem_wait_st();
+            if (__any_sync(0xffffffffu, tie)) {
+                // an exact tie in the past column: the literal walk (march_sweep) on a shared-memory copy, under the CTA's lock
+                if (lane == 0) { while (atomicCAS(&ctl.tie_lock, 0, 1) != 0) __nanosleep(100); __threadfence_block(); }
+                __syncwarp();
+                for (int q = 0; q < NB; q++) {
+                    float v[4], w[4];
+                    eikm::tmem_ld4(tp + 4 * q, v);
+                    if (s_tmem) eikm::tmem_ld4(tS + 4 * q, w);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) w[c] = S3[(long)(4 * q - 1 + c) * 32];
+                    }
+                    eikm::tmem_wait_ld(v, w);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { tieP[(long)(4 * q - 1 + c) * 32] = v[c]; tieS[(long)(4 * q - 1 + c) * 32] = w[c]; }
+                }
+                tieS[-64] = kInfM;
+                if (tie) { tieP[-32] = eikf::kStop; tieP[(long)(ke + 1) * 32] = eikf::kStop; }
+                int nohint = -1;
+                eikf::march_sweep(tie, tieP, tieC, tieS, ke, &nohint);
+                for (int q = 0; q < NB; q++) {
+                    float v[4];
+                    eikm::tmem_ld4(tc + 4 * q, v);
+                    eikm::tmem_wait_ld(v);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int k = 4 * q - 1 + c;
+                        if (tie && k >= 0 && k <= ke) v[c] = tieC[(long)k * 32];
+                    }
+                    eikm::tmem_st4(tc + 4 * q, v);
+                }
+                eikm::tmem_wait_st();
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); atomicExch(&ctl.tie_lock, 0); }
+            }
+            eikm::tmem_st1(tc, eikf::kEdge);
+            for (int k = ke + 1; k <= CA - 2; k++) eikm::tmem_st1(tc + k + 1, eikm::sentinel(k, ke));
+            eikm::tmem_wait_st();
+            for (int r = 0; r < b.n_rows; r++) {
+                float v = eikm::tmem_ld1(tc + b.rows[r] + 1);
+                eikm::tmem_wait_ld(v);
+                if (need) t.out[(long)r * t.out_rstride + line] = v;
+            }
+            const uint32_t tt = tp; tp = tc; tc = tt;
+        }
+        pipe_release(&ctl.tset_free[quarter], ts, lane);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) eikm::tmem_dealloc<512>(ctl.tmem);
+}
+
+bool eik_pipe_supported(int nxmod, int nz)
+{
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("MCMCEQ_EIKONAL_PIPE");
+        enabled = (e && e[0] == '0') ? 0 : 1;     // on unless MCMCEQ_EIKONAL_PIPE=0
+    }
+    return enabled && eik_fast_supported(nxmod, nz) && nz + 2 <= kPipeCA;
+}
+
+cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t stream)
+{
+    if (b.src_iz || b.full_out || !task_counter || !b.tie_scratch) return cudaErrorInvalidValue;
+    const eikf::Dims D = fast_dims(b.nxmod, b.nz);
+    const size_t slice = fast_smem_floats_per_warp(D) * sizeof(float);
+    const size_t tie = 0;      // the tie scratch lives in global memory (b.tie_scratch)
+    int dev = 0, sms = 148, smem_max = 232448;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int n_slices = (int)(((size_t)smem_max - tie - 256) / slice);
+    if (n_slices > 12) n_slices = 12;
+    if (n_slices < 2) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)n_slices * slice + tie;
+    static size_t configured = 0;     // largest dynamic shared-memory size the kernel has been opted in for
+    if (smem > configured) {
+        cudaFuncSetAttribute(eik_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(eik_pipe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        configured = smem;
+    }
+    const int n_tasks = (b.n_items * b.nz + 31) / 32;
+    // per-warp global window: the scratch was sized for max_warps warps of the generic kernel
+    const size_t have = (size_t)b.max_warps * eik_scratch_floats_per_warp(b.nxmod, b.nz);
+    const long warps_by_scratch = (long)(have / fast_scratch_floats_per_warp(D));
+    int blocks = (n_tasks + kPipeWarps - 1) / kPipeWarps;
+    if (blocks > sms) blocks = sms;
+    if ((long)blocks * kPipeWarps > warps_by_scratch) blocks = (int)(warps_by_scratch / kPipeWarps);
+    if (blocks < 1) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(task_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    eik_pipe_kernel<<<blocks, kPipeWarps * 32, smem, stream>>>(b, D, n_slices, task_counter);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static int split_cols(int nz) { return nz + 2 <= 64 ? 128 : nz + 2 <= 128 ? 256 : nz + 2 <= 256 ? 512 : 0; }
 
 // Off unless MCMCEQ_EIKONAL_SPLIT=1: measured on B200 (profiles/README.md, r1t) the two kernels take 6.6 ms (box, alone it
@@ -339,6 +577,8 @@ bool eik_split_supported(int nxmod, int nz)
     }
     return enabled && eik_fast_supported(nxmod, nz) && split_cols(nz) != 0;
 }
+
+size_t eik_pipe_tie_floats() { return 148 * 2 * kPipeTieFloats; }
 
 size_t eik_hand_floats(int max_solves, int nz) { return (((size_t)max_solves + 31) / 32) * 32 * (size_t)nz; }
 
@@ -438,6 +678,17 @@ cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream)
     if (force_generic < 0) {
         const char* e = getenv("MCMCEQ_EIKONAL");
         force_generic = (e && strcmp(e, "generic") == 0) ? 1 : 0;
+    }
+    if (!force_generic && b.task_counter && b.tie_scratch && !b.src_iz && !b.full_out && eik_pipe_supported(b.nxmod, b.nz)) {
+        // worth it (and the per-warp scratch windows suffice) only when there is work for every warp of every SM
+        const eikf::Dims D = fast_dims(b.nxmod, b.nz);
+        const size_t have = (size_t)b.max_warps * eik_scratch_floats_per_warp(b.nxmod, b.nz);
+        const long n_tasks = ((long)b.n_items * b.nz + 31) / 32;
+        if ((long)(have / fast_scratch_floats_per_warp(D)) >= 148L * kPipeWarps && n_tasks >= 148L * kPipeWarps) {
+            EikBatch piped = b;
+            piped.hand_col = nullptr; piped.hand_x1 = nullptr;
+            return eik_launch_pipe(piped, b.task_counter, stream);
+        }
     }
     if (!force_generic && b.hand_x1 && b.hand_col && !b.src_iz && !b.full_out && eik_split_supported(b.nxmod, b.nz))
         return eik_launch_split(b, stream);

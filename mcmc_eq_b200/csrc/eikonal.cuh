@@ -29,6 +29,8 @@ struct EikBatch {
     // (-1: nothing left to march); the march kernel continues from there.  Both nullptr: one fused kernel.
     float* hand_col;
     int32_t* hand_x1;
+    int32_t* task_counter;    // [1] device: work counter of the pipelined kernel (eik_launch_pipe), or nullptr
+    float* tie_scratch;       // device, eik_pipe_tie_floats() floats: per-CTA scratch of the pipelined kernel's tie fallback
     // Outputs (device).  full_out: [n_solves][nxmod*nz] in the reference layout (x*nz+y).
     float* full_out;
     // Receiver-row tables: table of item i starts at row_out[i] (or row_out_base + i*row_item_stride
@@ -59,6 +61,10 @@ cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream);
 bool eik_split_supported(int nxmod, int nz);
 size_t eik_hand_floats(int max_solves, int nz);
 cudaError_t eik_launch_split(const EikBatch& b, cudaStream_t stream);
+// One persistent CTA per SM, 16 warps: box phases on a pool of shared-memory slices, marches on a pool of TMEM sets.
+bool eik_pipe_supported(int nxmod, int nz);
+size_t eik_pipe_tie_floats();
+cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t stream);
 // Picks the fast kernel when the grid allows it (MCMCEQ_EIKONAL=generic forces the generic one).
 cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream);
 // Regrouping of the solves of a table-mode batch (see EikBatch::order).  `work` holds the sort buffers:

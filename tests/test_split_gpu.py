@@ -23,13 +23,13 @@ for name in ("example2", "example"):
     d = tempfile.mkdtemp(prefix="mqsp_")
     cfgp, pkp = inputs.materialise(name, d)
     cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
-    n = 70                                        # not a multiple of 32: ragged last warp
+    n = int(sys.argv[2])                          # not a multiple of 32: ragged last warp
     smp = mq.Sampler(cfg, pk, n, 0, 1)
     rng = np.random.default_rng(4)
     st = fh.random_states(rng, cfg, pk, n, kind="posterior") if name == "example" else fh.random_states(rng, cfg, pk, n, kind="lvz")
     mf, org = smp.forward_host(fh.fill_models(smp.new_models(32), st), 3)
     res, tp = smp.predictions(3)
-    smp.init_chains(); smp.step(12, "PVMBDQ")
+    smp.init_chains(); smp.step(6, "PVMBDQ")
     c, ll, rms = smp.stats()
     out[name + "_mf"] = mf; out[name + "_org"] = org; out[name + "_tp"] = tp; out[name + "_ll"] = ll; out[name + "_c"] = c
     smp.close()
@@ -37,9 +37,9 @@ np.savez(sys.argv[1], **out)
 """
 
 
-def _run(path, split):
-    env = dict(os.environ, MCMCEQ_EIKONAL_SPLIT="1" if split else "0")
-    r = subprocess.run([sys.executable, "-c", SCRIPT % util.ROOT, path], env=env, capture_output=True, text=True, timeout=600)
+def _run(path, split, pipe=False, n=70):
+    env = dict(os.environ, MCMCEQ_EIKONAL_SPLIT="1" if split else "0", MCMCEQ_EIKONAL_PIPE="1" if pipe else "0")
+    r = subprocess.run([sys.executable, "-c", SCRIPT % util.ROOT, path, str(n)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
     return dict(np.load(path))
 
@@ -50,3 +50,13 @@ def test_tensor_memory_march_is_bit_identical_to_the_fused_kernel(tmp_path):
     for k in a:
         assert np.array_equal(a[k], b[k]), k
     assert np.isfinite(a["example_mf"]).all() and a["example2_c"][:, 17].sum() > 0
+
+
+def test_pipelined_kernel_is_bit_identical_to_the_fused_kernel(tmp_path):
+    """MCMCEQ_EIKONAL_PIPE=1: one persistent CTA per SM, 16 warps sharing a pool of shared-memory slices (box phase) and a
+    pool of TMEM sets (march)."""
+    # the pipelined kernel only takes launches with work for all 148 x 16 warps: 1230 chains x 2 phases x 61 depths
+    a = _run(str(tmp_path / "fused.npz"), False, n=1230)
+    b = _run(str(tmp_path / "pipe.npz"), False, pipe=True, n=1230)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), (k, int((a[k] != b[k]).sum()), a[k].size, float(np.nanmax(np.abs(a[k].astype(float) - b[k].astype(float)))))
