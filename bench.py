@@ -334,7 +334,8 @@ def main():
         t_launch = eik_ms / eik_n / 1000.0
         achieved = alg_bytes_per_solve * solves_per_launch / t_launch / 1e9
         smem_alg = 32.0 * nxmod * nz * solves_per_launch / t_launch / 1e9
-        kernel = "eik_generic_kernel" if os.environ.get("MCMCEQ_EIKONAL") == "generic" else "eik_fast_kernel"
+        kernel = ("eik_generic_kernel" if os.environ.get("MCMCEQ_EIKONAL") == "generic" else
+                  "eik_fast_kernel" if os.environ.get("MCMCEQ_EIKONAL_PIPE") == "0" else "eik_pipe_kernel")
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": kernel_traffic(kernel, solves_per_launch), "peak_source": peak_src,
                     "algorithmic_bytes_per_solve": alg_bytes_per_solve, "solves_per_launch": int(solves_per_launch),

@@ -356,7 +356,7 @@ __device__ __forceinline__ int pipe_acquire(unsigned* mask, int lane)
                 const int bit = __ffs(m) - 1;
                 if (atomicAnd(mask, ~(1u << bit)) & (1u << bit)) { got = bit; break; }
             } else {
-                __nanosleep(100);
+                __nanosleep(20000);
             }
         }
         __threadfence_block();
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
             eikm::tmem_wait_st();
             if (__any_sync(0xffffffffu, tie)) {
                 // an exact tie in the past column: the literal walk (march_sweep) on a shared-memory copy, under the CTA's lock
-                if (lane == 0) { while (atomicCAS(&ctl.tie_lock, 0, 1) != 0) __nanosleep(100); __threadfence_block(); }
+                if (lane == 0) { while (atomicCAS(&ctl.tie_lock, 0, 1) != 0) __nanosleep(500); __threadfence_block(); }
                 __syncwarp();
                 for (int q = 0; q < NB; q++) {
                     float v[4], w[4];
