@@ -107,7 +107,7 @@ extern "C" int mq_destroy(mq_handle* hh)
     free_view(&h->cur_view); free_view(&h->prop_view);
     cudaFree(h->evq); cudaFree(h->oq); cudaFree(h->mf_eval); cudaFree(h->resid); cudaFree(h->tpred);
     cudaFree(h->item_chain); cudaFree(h->item_phase); cudaFree(h->n_items); cudaFree(h->slow); cudaFree(h->item_tab);
-    cudaFree(h->solve_status); cudaFree(h->scratch); cudaFree(h->eik_order); cudaFree(h->eik_order_work); cudaFree(h->eik_hand_col); cudaFree(h->eik_hand_x1); cudaFree(h->eik_task_counter); cudaFree(h->eik_tie_scratch);
+    cudaFree(h->solve_status); cudaFree(h->scratch); cudaFree(h->eik_order); cudaFree(h->eik_order_work); cudaFree(h->eik_task_counter); cudaFree(h->eik_tie_scratch);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete hh;
     return MQ_OK;
@@ -245,11 +245,6 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
             TRY(cudaMalloc((void**)&h->eik_order, (((size_t)max_solves + 31) / 32 * 32) * sizeof(int32_t)));
         }
         if (eik_pipe_supported(h->nxmod, h->nz)) { TRY(dalloc(&h->eik_task_counter, 1)); TRY(dalloc(&h->eik_tie_scratch, eik_pipe_tie_floats())); }
-        if (eik_split_supported(h->nxmod, h->nz)) {
-            const int max_solves = 2 * n_chains * h->nz;
-            TRY(cudaMalloc((void**)&h->eik_hand_col, eik_hand_floats(max_solves, h->nz) * sizeof(float)));
-            TRY(cudaMalloc((void**)&h->eik_hand_x1, (((size_t)max_solves + 31) / 32 * 32) * sizeof(int32_t)));
-        }
     }
     TRY(cudaStreamSynchronize(s));
 #undef TRY

@@ -1,22 +1,17 @@
-// eik_march.cuh -- the column march of the eikonal solver with its two columns in TENSOR MEMORY (sm_100a, device only).
+// eik_march.cuh -- the column march of the eikonal solver with its columns in TENSOR MEMORY (sm_100a, device only).
 //
 // After the expanding box spans the whole depth range a solve is a march over columns: column x+1 from column x and the
 // slowness column (eik_fast.cuh: march_sweep3).  Its accesses are warp-uniform in the index -- every lane is at the same
 // depth at the same time -- which is exactly the 32x32b shape of tcgen05.ld / tcgen05.st: thread i of a warp reads or
-// writes 32 bits of TMEM lane (32*(warp%4) + i) at a column address common to the warp.  So the past and the current
-// column live in tensor memory, node k of a lane at column k+1 of that lane, and
-//   * the shared memory they occupied is gone from this kernel: 8.4 KB per warp (the slowness column) instead of 24.7 KB,
-//     16 warps per SM instead of 9 -- the march was issue-limited at 2.25 warps per scheduler;
-//   * four consecutive nodes move per instruction (.x4): 2 loads + 2 stores per 8 node updates instead of 12 + 8;
+// writes 32 bits of TMEM lane (32*(warp%4) + i) at a column address common to the warp.  So the past column, the current
+// column and the slowness column of a marching warp live in tensor memory, node k of a lane at column k+1 of that lane:
+//   * a marching warp needs no shared memory, which goes to the warps that are in their box phase (per-lane indices):
+//     eik_pipe_kernel (eikonal.cu) runs 16 warps per SM on 9 shared-memory slices + 8 TMEM sets instead of 9 warps;
+//   * four consecutive nodes move per instruction (.x4);
 //   * TMEM load latency is 12 cycles against 29 for shared memory.
-// The box phase (per-lane indices, needs shared memory) runs in its own kernel (eik_box_kernel, eikonal.cu) and hands
-// each solve's last column over through global memory (62 floats per solve).
-//
-// Layout: one CTA = 4 warps = the 4 lane quarters of TMEM; the CTA allocates 2*CA columns (CA = 64 for nz <= 62):
-// array 0 = columns [0, CA), array 1 = [CA, 2*CA); past and current column alternate between them.  A column holds the
-// nodes -1 .. CA-2: nodes -1 and ke+1.. carry sentinels larger than any time (strictly increasing, so they never tie),
-// which end the chains exactly where march_sweep3's kEdge slots do.  Arithmetic: chain_a_node / chain_b_node of
-// eik_fast.cuh, unchanged -- results are bit-identical to the fused kernel's.
+// A column array holds the nodes -1 .. CA-2 (CA = 64 for nz <= 62): nodes -1 and ke+1.. carry sentinels larger than any
+// time (strictly increasing, so they never tie), which end the chains exactly where march_sweep3's kEdge slots do.
+// Arithmetic: chain_a_node / chain_b_node of eik_fast.cuh, unchanged -- results are bit-identical to the fused kernel's.
 #pragma once
 #include <stdint.h>
 

@@ -126,10 +126,6 @@ __global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims 
             }
             if (b.full_out) t.full = b.full_out + (size_t)g * nodes;
         }
-        if (b.hand_x1) {   // split mode: every lane of the task owns a slot, valid or not
-            t.hand_col = b.hand_col + ((size_t)task * b.nz) * 32 + lane;
-            t.hand_x1 = b.hand_x1 + (size_t)task * 32 + lane;
-        }
         const int rc = eikf::solve_warp(D, L, t, b.rows, b.n_rows);
         if (t.valid) {
             if (b.status) b.status[g] = rc;
@@ -215,117 +211,6 @@ cudaError_t eik_order_tasks(const EikBatch& b, int32_t* order, void* work, size_
     return e;
 }
 
-// ---- the march kernel (columns in tensor memory) --------------------------------------------------------------------
-// One CTA = 4 warps = the 4 lane quarters of TMEM, each warp marches 32 solves on its own.  Shared memory: the slowness
-// column of every lane ([k][lane], k = -2 .. CA-1) and one scratch pair of columns per CTA for the literal walk of a
-// column with an exact tie (4 in 100 000), taken under a lock.
-template <int COLS>
-__global__ void __launch_bounds__(128) eik_march_kernel(EikBatch b)
-{
-    constexpr int CA = COLS / 2, NB = CA / 4;
-    extern __shared__ float smem_m[];
-    __shared__ uint32_t s_tmem;
-    __shared__ int s_lock;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0) eikm::tmem_alloc<COLS>(&s_tmem);
-    if (threadIdx.x == 0) s_lock = 0;
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tbase = s_tmem + ((uint32_t)(warp * 32) << 16);
-    float* S = smem_m + (size_t)warp * (CA + 2) * 32 + 2 * 32 + lane;        // cell k at S[k*32]
-    float* scrP = smem_m + (size_t)4 * (CA + 2) * 32 + 32 + lane;            // node k at scrP[k*32], k = -1 .. CA-2
-    float* scrC = scrP + (size_t)CA * 32;
-    const int nz = b.nz, ke = nz - 1, mx = b.nxmod - 1;
-    const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
-    const int n_solves = n_items * nz;
-    const int n_tasks = (n_solves + 31) >> 5;
-
-    for (int task = blockIdx.x * 4 + warp; task < n_tasks; task += gridDim.x * 4) {
-        const int j = task * 32 + lane;
-        const int g = b.order ? b.order[j] : j;
-        const bool valid = g >= 0 && g < n_solves;
-        const int x1 = valid ? b.hand_x1[j] : -1;
-        const bool live = x1 >= 0 && x1 < mx;
-        if (!__any_sync(0xffffffffu, live)) continue;
-        const int iz = valid ? g / n_items : 0, item = valid ? g - iz * n_items : 0;
-        const float* slow = b.slow + (size_t)item * nz;
-        float* out = nullptr;
-        const long rstride = (long)nz * b.xpitch;
-        if (valid) {
-            float* tab = b.row_out ? b.row_out[item] : b.row_out_base + (size_t)item * b.row_item_stride;
-            out = tab + (size_t)iz * b.xpitch;
-        }
-        // slowness cells -> shared; the dummy row and everything outside the model is INF (src/time_2d.c:489-492)
-        for (int k = -2; k < CA; k++) S[(long)k * 32] = (live && k >= 0 && k < ke) ? slow[k] : kInfM;
-        // last column of the box phase -> tensor memory array 0, sentinels round it
-        const float* hc = b.hand_col + ((size_t)task * nz) * 32 + lane;
-        for (int q = 0; q < NB; q++) {
-            float v[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int k = 4 * q - 1 + c;
-                v[c] = (k >= 0 && k <= ke) ? (live ? hc[(size_t)k * 32] : 0.f) : eikm::sentinel(k, ke);
-            }
-            eikm::tmem_st4(tbase + 4 * q, v);
-        }
-        eikm::tmem_wait_st();
-        __syncwarp();
-        uint32_t tp = tbase, tc = tbase + CA;
-        const int xlo = __reduce_min_sync(0xffffffffu, live ? x1 : 0x7fffffff);
-        const int xhi = __reduce_max_sync(0xffffffffu, live ? x1 : -1);
-        for (int line = xlo + 1; line <= mx; line++) {
-            const bool need = live && line > x1;
-            const bool tie = (line <= xhi) ? eikm::tmem_sweep<NB, true, false>(need, tp, tc, S, 0u) : eikm::tmem_sweep<NB, false, false>(need, tp, tc, S, 0u);
-            eikm::tmem_wait_st();
-            if (__any_sync(0xffffffffu, tie)) {
-                // an exact tie in the past column: follow the reference's order literally (march_sweep) on a shared-memory copy
-                if (lane == 0) while (atomicCAS(&s_lock, 0, 1) != 0) { }
-                __syncwarp();
-                for (int q = 0; q < NB; q++) {
-                    float v[4];
-                    eikm::tmem_ld4(tp + 4 * q, v);
-                    eikm::tmem_wait_ld(v);
-#pragma unroll
-                    for (int c = 0; c < 4; c++) scrP[(long)(4 * q - 1 + c) * 32] = v[c];
-                }
-                if (tie) { scrP[-32] = eikf::kStop; scrP[(long)(ke + 1) * 32] = eikf::kStop; }
-                int nohint = -1;
-                eikf::march_sweep(tie, scrP, scrC, S, ke, &nohint);
-                for (int q = 0; q < NB; q++) {
-                    float v[4];
-                    eikm::tmem_ld4(tc + 4 * q, v);
-                    eikm::tmem_wait_ld(v);
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int k = 4 * q - 1 + c;
-                        if (tie && k >= 0 && k <= ke) v[c] = scrC[(long)k * 32];
-                    }
-                    eikm::tmem_st4(tc + 4 * q, v);
-                }
-                eikm::tmem_wait_st();
-                __syncwarp();
-                if (lane == 0) atomicExch(&s_lock, 0);
-            }
-            // the sentinel nodes of the new column
-            eikm::tmem_st1(tc, eikf::kEdge);
-            for (int k = ke + 1; k <= CA - 2; k++) eikm::tmem_st1(tc + k + 1, eikm::sentinel(k, ke));
-            eikm::tmem_wait_st();
-            // receiver rows of this column
-            for (int r = 0; r < b.n_rows; r++) {
-                float v = eikm::tmem_ld1(tc + b.rows[r] + 1);
-                eikm::tmem_wait_ld(v);
-                if (need) out[(long)r * rstride + line] = v;
-            }
-            const uint32_t t = tp; tp = tc; tc = t;
-        }
-        __syncwarp();
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) eikm::tmem_dealloc<COLS>(s_tmem);
-}
-
 // ---- the pipelined kernel: box phase in shared memory, march in tensor memory, in ONE persistent CTA per SM --------------
 // The fused kernel holds 9 warps per SM because every warp keeps 24.7 KB of shared memory for its whole life, although it
 // only needs it for the box phase (per-lane indices); the march (warp-uniform indices) can live in TMEM.  Here 16 warps
@@ -337,6 +222,7 @@ __global__ void __launch_bounds__(128) eik_march_kernel(EikBatch b)
 // else), holders of a TMEM set never wait for a slice: no cycle, no deadlock.
 constexpr int kPipeWarps = 16;
 constexpr int kPipeCA = 64;          // nodes -1 .. 62 per TMEM column array: nz <= 62
+constexpr int kPipeMaxCtas = 256;    // one CTA per SM; the tie scratch is sized for this many
 constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time columns + slowness column of the tie scratch
 
 struct PipeCtl {
@@ -563,74 +449,7 @@ cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t s
     return cudaGetLastError();
 }
 
-static int split_cols(int nz) { return nz + 2 <= 64 ? 128 : nz + 2 <= 128 ? 256 : nz + 2 <= 256 ? 512 : 0; }
-
-// Off unless MCMCEQ_EIKONAL_SPLIT=1: measured on B200 (profiles/README.md, r1t) the two kernels take 6.6 ms (box, alone it
-// is latency bound at 31 % issue) + 5.2 ms (march, 80 % issue at 16 warps per SM) against 11.05 ms for the fused kernel,
-// in which the march of some warps hides the latencies of the box phase of others.
-bool eik_split_supported(int nxmod, int nz)
-{
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("MCMCEQ_EIKONAL_SPLIT");
-        enabled = (e && e[0] == '1') ? 1 : 0;
-    }
-    return enabled && eik_fast_supported(nxmod, nz) && split_cols(nz) != 0;
-}
-
-size_t eik_pipe_tie_floats() { return 148 * 2 * kPipeTieFloats; }
-
-size_t eik_hand_floats(int max_solves, int nz) { return (((size_t)max_solves + 31) / 32) * 32 * (size_t)nz; }
-
-template <int COLS>
-static cudaError_t launch_march(const EikBatch& b, int n_tasks, cudaStream_t stream)
-{
-    constexpr int CA = COLS / 2;
-    const size_t smem = ((size_t)4 * (CA + 2) * 32 + (size_t)2 * CA * 32) * sizeof(float);
-    static bool configured = false;
-    static int per_sm = 1, sms = 148;
-    if (!configured) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(eik_march_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(eik_march_kernel<COLS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        // Resident CTAs per SM from the kernel's own footprint (registers, shared memory, tensor-memory columns); the
-        // occupancy API answers 1 for a kernel that allocates tensor memory, whatever it allocates.
-        cudaFuncAttributes fa;
-        int smem_sm = 233472, regs_sm = 65536;
-        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
-        per_sm = 512 / COLS;
-        if (cudaFuncGetAttributes(&fa, eik_march_kernel<COLS>) == cudaSuccess) {
-            const int by_regs = regs_sm / (128 * (fa.numRegs > 0 ? fa.numRegs : 128));
-            const int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));
-            if (by_regs < per_sm) per_sm = by_regs;
-            if (by_smem < per_sm) per_sm = by_smem;
-        }
-        if (per_sm < 1) per_sm = 1;
-        configured = true;
-    }
-    int blocks = (n_tasks + 3) / 4;
-    if (blocks > sms * per_sm) blocks = sms * per_sm;
-    eik_march_kernel<COLS><<<blocks, 128, smem, stream>>>(b);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t eik_launch_split(const EikBatch& b, cudaStream_t stream)
-{
-    if (b.src_iz || b.full_out || !b.hand_col || !b.hand_x1) return cudaErrorInvalidValue;
-    cudaError_t e = eik_launch_fast(b, stream);           // box phase: the fast kernel in hand-over mode
-    if (e != cudaSuccess) return e;
-    const int n_tasks = (b.n_items * b.nz + 31) / 32;     // upper bound when n_items_dev is set
-    switch (split_cols(b.nz)) {
-    case 128: return launch_march<128>(b, n_tasks, stream);
-    case 256: return launch_march<256>(b, n_tasks, stream);
-    case 512: return launch_march<512>(b, n_tasks, stream);
-    default: return cudaErrorInvalidValue;
-    }
-}
+size_t eik_pipe_tie_floats() { return (size_t)kPipeMaxCtas * kPipeTieFloats; }
 
 int eik_fast_max_warps(int nxmod, int nz, int device)
 {
@@ -684,18 +503,17 @@ cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream)
         const eikf::Dims D = fast_dims(b.nxmod, b.nz);
         const size_t have = (size_t)b.max_warps * eik_scratch_floats_per_warp(b.nxmod, b.nz);
         const long n_tasks = ((long)b.n_items * b.nz + 31) / 32;
-        if ((long)(have / fast_scratch_floats_per_warp(D)) >= 148L * kPipeWarps && n_tasks >= 148L * kPipeWarps) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((long)(have / fast_scratch_floats_per_warp(D)) >= (long)sms * kPipeWarps && n_tasks >= (long)sms * kPipeWarps &&
+            sms <= kPipeMaxCtas) {
             EikBatch piped = b;
-            piped.hand_col = nullptr; piped.hand_x1 = nullptr;
             return eik_launch_pipe(piped, b.task_counter, stream);
         }
     }
-    if (!force_generic && b.hand_x1 && b.hand_col && !b.src_iz && !b.full_out && eik_split_supported(b.nxmod, b.nz))
-        return eik_launch_split(b, stream);
-    EikBatch fused = b;            // one kernel does everything: no hand-over
-    fused.hand_col = nullptr; fused.hand_x1 = nullptr;
-    if (!force_generic && eik_fast_supported(b.nxmod, b.nz)) return eik_launch_fast(fused, stream);
-    return eik_launch_generic(fused, stream);
+    if (!force_generic && eik_fast_supported(b.nxmod, b.nz)) return eik_launch_fast(b, stream);
+    return eik_launch_generic(b, stream);
 }
 
 }  // namespace mq

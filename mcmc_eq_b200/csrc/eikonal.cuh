@@ -24,11 +24,6 @@ struct EikBatch {
     // task j / 32 runs, or -1 (eik_order_tasks fills it: solves of one source depth that initialise and grow their
     // boxes alike are made neighbours so that the lanes of a warp stay in step).
     const int32_t* order;
-    // Table mode only: split execution (eik_launch_split).  The box kernel leaves, for the lane at position j of the
-    // execution order, its last column in hand_col[((j/32)*nz + k)*32 + j%32] and that column's index in hand_x1[j]
-    // (-1: nothing left to march); the march kernel continues from there.  Both nullptr: one fused kernel.
-    float* hand_col;
-    int32_t* hand_x1;
     int32_t* task_counter;    // [1] device: work counter of the pipelined kernel (eik_launch_pipe), or nullptr
     float* tie_scratch;       // device, eik_pipe_tie_floats() floats: per-CTA scratch of the pipelined kernel's tie fallback
     // Outputs (device).  full_out: [n_solves][nxmod*nz] in the reference layout (x*nz+y).
@@ -56,11 +51,6 @@ cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream);
 // is smaller (box window + refined grid) so the generic kernel's scratch always suffices.
 bool eik_fast_supported(int nxmod, int nz);
 cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream);
-// Box phase and march as two kernels, the march with its columns in tensor memory (eik_march.cuh).  Needs
-// b.hand_col / b.hand_x1, receiver-row output only (no full_out), nz <= 254.
-bool eik_split_supported(int nxmod, int nz);
-size_t eik_hand_floats(int max_solves, int nz);
-cudaError_t eik_launch_split(const EikBatch& b, cudaStream_t stream);
 // One persistent CTA per SM, 16 warps: box phases on a pool of shared-memory slices, marches on a pool of TMEM sets.
 bool eik_pipe_supported(int nxmod, int nz);
 size_t eik_pipe_tie_floats();

@@ -135,7 +135,7 @@ cudaError_t launch_tables(Handle* h, int max_items)
         if (e != cudaSuccess) return e;
         b.order = h->eik_order;
     }
-    b.hand_col = h->eik_hand_col; b.hand_x1 = h->eik_hand_x1; b.task_counter = h->eik_task_counter; b.tie_scratch = h->eik_tie_scratch;
+    b.task_counter = h->eik_task_counter; b.tie_scratch = h->eik_tie_scratch;
     return eik_launch(b, h->stream);
 }
 

@@ -106,9 +106,7 @@ struct Handle {
     int32_t* solve_status; // [1] min over solves
     float* scratch;      // eikonal scratch
     int scratch_warps;
-    float* eik_hand_col; // hand-over from the box kernel to the march kernel (eikonal.cuh), or nullptr
-    int32_t* eik_hand_x1;
-    int32_t* eik_task_counter;
+    int32_t* eik_task_counter;   // work counter and tie scratch of the pipelined eikonal kernel (eikonal.cuh), or nullptr
     float* eik_tie_scratch;
     int32_t* eik_order;  // [round_up(2n*nz, 32)] execution order of the solves of a table rebuild (eikonal.cuh), or nullptr
     void* eik_order_work;

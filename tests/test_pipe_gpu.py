@@ -1,7 +1,7 @@
-"""The optional two-kernel eikonal path (MCMCEQ_EIKONAL_SPLIT=1): box phase in shared memory, column march with its
-columns in tensor memory (csrc/eik_march.cuh: tcgen05.ld/st, 32x32b).  Same arithmetic as the fused kernel, so the class
-sums, origin times and per-pick predictions must be IDENTICAL bit for bit; run in a subprocess because the switch is read
-once per process."""
+"""The two eikonal kernels against each other: the pipelined kernel (default: box phases on a pool of shared-memory slices,
+column marches in tensor memory, csrc/eik_march.cuh: tcgen05.ld/st 32x32b) and the fused kernel (MCMCEQ_EIKONAL_PIPE=0:
+everything in shared memory).  Same arithmetic, so class sums, origin times, per-pick predictions and chain trajectories must
+be IDENTICAL bit for bit; each runs in its own subprocess because the switch is read once per process."""
 import os
 import subprocess
 import sys
@@ -37,26 +37,17 @@ np.savez(sys.argv[1], **out)
 """
 
 
-def _run(path, split, pipe=False, n=70):
-    env = dict(os.environ, MCMCEQ_EIKONAL_SPLIT="1" if split else "0", MCMCEQ_EIKONAL_PIPE="1" if pipe else "0")
+def _run(path, pipe, n):
+    env = dict(os.environ, MCMCEQ_EIKONAL_PIPE="1" if pipe else "0")
     r = subprocess.run([sys.executable, "-c", SCRIPT % util.ROOT, path, str(n)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
     return dict(np.load(path))
 
 
-def test_tensor_memory_march_is_bit_identical_to_the_fused_kernel(tmp_path):
-    a = _run(str(tmp_path / "fused.npz"), False)
-    b = _run(str(tmp_path / "split.npz"), True)
-    for k in a:
-        assert np.array_equal(a[k], b[k]), k
-    assert np.isfinite(a["example_mf"]).all() and a["example2_c"][:, 17].sum() > 0
-
-
 def test_pipelined_kernel_is_bit_identical_to_the_fused_kernel(tmp_path):
-    """MCMCEQ_EIKONAL_PIPE=1: one persistent CTA per SM, 16 warps sharing a pool of shared-memory slices (box phase) and a
-    pool of TMEM sets (march)."""
+    """One persistent CTA per SM, 16 warps sharing a pool of shared-memory slices (box phase) and a pool of TMEM sets (march)."""
     # the pipelined kernel only takes launches with work for all 148 x 16 warps: 1230 chains x 2 phases x 61 depths
-    a = _run(str(tmp_path / "fused.npz"), False, n=1230)
-    b = _run(str(tmp_path / "pipe.npz"), False, pipe=True, n=1230)
+    a = _run(str(tmp_path / "fused.npz"), False, 1230)
+    b = _run(str(tmp_path / "pipe.npz"), True, 1230)
     for k in a:
         assert np.array_equal(a[k], b[k]), (k, int((a[k] != b[k]).sum()), a[k].size, float(np.nanmax(np.abs(a[k].astype(float) - b[k].astype(float)))))
