@@ -140,40 +140,61 @@ cudaError_t launch_tables(Handle* h, int max_items)
 }
 
 // ---- travel-time lookup -------------------------------------------------------------------
-// Bilinear interpolation weights of (dist, z) in a [nz][xp] receiver-row table; the same
-// arithmetic as traveltimet (src/interpol.c:56-80): float corner products summed left to right,
-// the 1/(dx*dy) prefactor in double.
-struct Bilinear {
-    int m1, iz1;
-    float a, b, c, d;   // x2-x, x-x1, y2-y, y-y1
+// Bilinear interpolation of (dist, z) in a [nz][xp] receiver-row table; the same arithmetic as traveltimet
+// (src/interpol.c:56-80): float corner products summed left to right, the 1/(dx*dy) prefactor in double.  The depth part
+// is the same for every pick of an event and is set up once per warp; 1/(x2-x1)/(y2-y1) is only divided out per pick when
+// the float difference x2-x1 is not the grid spacing itself (never for a power-of-two spacing).
+struct BilinearZ {
+    int iz1;
+    float c, d, dyf;    // y2-y, y-y1, y2-y1
+    double pref0;       // 1 / h / (y2-y1)
+    bool oob;
+};
+
+__device__ __forceinline__ BilinearZ bilinear_depth(float z, float hgrid, float z0, int nz)
+{
+    BilinearZ w;
+    const float y = __fsub_rn(z, z0);
+    w.iz1 = (int)__fdiv_rn(y, hgrid);
+    w.oob = w.iz1 >= nz - 1;
+    const float y1 = __fmul_rn((float)w.iz1, hgrid), y2 = __fmul_rn((float)(w.iz1 + 1), hgrid);
+    w.c = __fsub_rn(y2, y);
+    w.d = __fsub_rn(y, y1);
+    w.dyf = __fsub_rn(y2, y1);
+    w.pref0 = 1.0 / (double)hgrid / (double)w.dyf;
+    return w;
+}
+
+struct BilinearX {
+    int m1;
+    float a, b;         // x2-x, x-x1
     double pref;
     bool oob;
 };
 
-__device__ __forceinline__ Bilinear bilinear_setup(float dist, float z, float hgrid, float z0, int nxmod, int nz)
+// rh = 1/hgrid, used instead of the division when hgrid is a power of two (bit-identical then)
+__device__ __forceinline__ BilinearX bilinear_dist(const BilinearZ& wz, float dist, float hgrid, float rh, bool h_pow2, int nxmod)
 {
-    Bilinear w;
-    w.m1 = (int)__fdiv_rn(dist, hgrid);
-    const float y = __fsub_rn(z, z0);
-    w.iz1 = (int)__fdiv_rn(y, hgrid);
-    w.oob = (w.m1 >= nxmod - 1 || w.iz1 >= nz - 1);
+    BilinearX w;
+    w.m1 = (int)(h_pow2 ? __fmul_rn(dist, rh) : __fdiv_rn(dist, hgrid));
+    w.oob = wz.oob || w.m1 >= nxmod - 1;
     const float x1 = __fmul_rn((float)w.m1, hgrid), x2 = __fmul_rn((float)(w.m1 + 1), hgrid);
-    const float y1 = __fmul_rn((float)w.iz1, hgrid), y2 = __fmul_rn((float)(w.iz1 + 1), hgrid);
-    w.a = __fsub_rn(x2, dist); w.b = __fsub_rn(dist, x1);
-    w.c = __fsub_rn(y2, y);    w.d = __fsub_rn(y, y1);
-    w.pref = 1.0 / (double)__fsub_rn(x2, x1) / (double)__fsub_rn(y2, y1);
+    w.a = __fsub_rn(x2, dist);
+    w.b = __fsub_rn(dist, x1);
+    const float dxf = __fsub_rn(x2, x1);
+    w.pref = (dxf == hgrid) ? wz.pref0 : 1.0 / (double)dxf / (double)wz.dyf;
     return w;
 }
 
-__device__ __forceinline__ float bilinear_eval(const Bilinear& w, const float* __restrict__ row, int xp)
+// row: the [nz][xp] table of one receiver row, already offset to depth row iz1
+__device__ __forceinline__ float bilinear_eval(const BilinearZ& wz, const BilinearX& w, const float* __restrict__ row, int xp)
 {
-    if (w.oob) return 1e30f;
-    const float* p = row + (size_t)w.iz1 * xp + w.m1;
+    const float* p = row + w.m1;
     const float v1 = __ldg(p), v2 = __ldg(p + 1), v3 = __ldg(p + xp), v4 = __ldg(p + xp + 1);
-    float s = __fmul_rn(__fmul_rn(v1, w.a), w.c);
-    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v2, w.b), w.c));
-    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v3, w.a), w.d));
-    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v4, w.b), w.d));
+    float s = __fmul_rn(__fmul_rn(v1, w.a), wz.c);
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v2, w.b), wz.c));
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v3, w.a), wz.d));
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(v4, w.b), wz.d));
     return (float)(w.pref * (double)s);
 }
 
@@ -187,8 +208,8 @@ __device__ __forceinline__ float warp_sum(float v)
 // One warp per (chain, event): lanes stride over the event's picks (P first, then S).
 struct MisfitParams {
     int n, ne, ns, np, nz, nxmod, xp, md;
-    float hgrid, z0;
-    int eikonal, scor_flag;
+    float hgrid, z0, rh;
+    int eikonal, scor_flag, h_pow2;
     size_t tab_stride;
     DevPicks pk;
     EvalView v;
@@ -201,7 +222,7 @@ struct MisfitParams {
     int32_t* err;
 };
 
-__global__ void __launch_bounds__(128) misfit_kernel(MisfitParams p)
+__global__ void __launch_bounds__(128, 8) misfit_kernel(MisfitParams p)
 {
     const int lane = threadIdx.x & 31;
     const long task = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -242,6 +263,10 @@ __global__ void __launch_bounds__(128) misfit_kernel(MisfitParams p)
         v0s = __fdiv_rn(v0p, p.vpvs[mo + k]);
     }
 
+    BilinearZ wz;
+    if (p.eikonal != 0) wz = bilinear_depth(ez, p.hgrid, p.z0, p.nz);
+    else { wz.iz1 = 0; wz.c = wz.d = wz.dyf = 0.f; wz.pref0 = 0.0; wz.oob = false; }
+    const size_t zoff = (size_t)(wz.oob ? 0 : wz.iz1) * p.xp;
     float sum = 0.f;
     bool oob = false;         // a pick fell outside the table (1e30 sentinel of src/interpol.c:64-65)
     unsigned present = 0u;    // classes that occur in this event
@@ -254,11 +279,11 @@ __global__ void __launch_bounds__(128) misfit_kernel(MisfitParams p)
             const float r2 = __fadd_rn(__fmul_rn(dist, dist), __fmul_rn(ez, ez));
             tt = (float)(sqrt((double)r2) / (double)(isS ? v0s : v0p));
         } else {
-            const Bilinear w = bilinear_setup(dist, ez, p.hgrid, p.z0, p.nxmod, p.nz);
+            const BilinearX w = bilinear_dist(wz, dist, p.hgrid, p.rh, p.h_pow2 != 0, p.nxmod);
             oob = oob || w.oob;
-            const float* row = (isS ? tabS : tabP) + (size_t)p.pk.r0[j] * rowsz;
-            const float t1 = bilinear_eval(w, row, p.xp);
-            const float t2 = bilinear_eval(w, row + rowsz, p.xp);
+            const float* row = (isS ? tabS : tabP) + (size_t)p.pk.r0[j] * rowsz + zoff;
+            const float t1 = w.oob ? 1e30f : bilinear_eval(wz, w, row, p.xp);
+            const float t2 = w.oob ? 1e30f : bilinear_eval(wz, w, row + rowsz, p.xp);
             tt = __fadd_rn(__fmul_rn(t1, p.pk.w1[j]), __fmul_rn(t2, p.pk.w2[j]));
         }
         const int st = p.pk.st_id[j];
@@ -316,7 +341,9 @@ cudaError_t launch_misfit(Handle* h, const EvalView& v)
 {
     MisfitParams p;
     p.n = h->n; p.ne = h->ne; p.ns = h->ns; p.np = h->np; p.nz = h->nz; p.nxmod = h->nxmod; p.xp = h->xp; p.md = h->md;
-    p.hgrid = h->cfg.grid.h; p.z0 = h->cfg.grid.z0; p.eikonal = h->cfg.eikonal; p.scor_flag = h->cfg.scor_flag;
+    p.hgrid = h->cfg.grid.h; p.z0 = h->cfg.grid.z0; p.rh = 1.0f / p.hgrid;
+    { int ex = 0; p.h_pow2 = (p.hgrid > 0.f && frexpf(p.hgrid, &ex) == 0.5f) ? 1 : 0; }
+    p.eikonal = h->cfg.eikonal; p.scor_flag = h->cfg.scor_flag;
     p.tab_stride = h->tab_stride; p.pk = h->pk; p.v = v; p.dim = h->dim; p.z = h->z; p.vp = h->vp; p.vpvs = h->vpvs;
     p.eq = h->eq; p.pres = h->pres; p.sres = h->sres; p.tab = h->tab; p.evsum = h->evsum; p.origin = h->origin;
     p.evq = h->evq; p.oq = h->oq; p.resid = h->resid; p.tpred = h->want_pred ? h->tpred : nullptr; p.err = h->err;
