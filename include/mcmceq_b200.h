@@ -54,7 +54,7 @@ typedef struct mq_config {
     float inv_control;                     /* 27, as written in the file (sign = LVZ switch) */
     int32_t reference_station, scor_flag;  /* 28      */
     float ref_statcor_P, ref_statcor_S;    /* 28      */
-    int32_t tria;                          /* 29 (only 0 = Voronoi is implemented) */
+    int32_t tria;                          /* 29: 0 = Voronoi cells, 1 = linear gradients between nuclei */
     int32_t j_max_start, j_max_main;       /* 30      */
     int32_t deci;                          /* 31      */
     int32_t true_random, eikonal;          /* 32      */

@@ -119,7 +119,7 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
     if (!cfg || !pk || !out || n_chains < 1) { set_error("mq_create: bad argument"); return MQ_ERR_ARG; }
     const mq_grid& g = cfg->grid;
     if (g.nz < 2 || g.nx < 1 || g.ny < 1 || !(g.h > 0.f)) { set_error("mq_create: bad grid"); return MQ_ERR_ARG; }
-    if (cfg->tria != 0) { set_error("mq_create: TRIA=1 (linear-gradient models) is not implemented"); return MQ_ERR_UNSUPPORTED; }
+    if (cfg->tria != 0 && cfg->tria != 1) { set_error("mq_create: config line 29 (TRIA) must be 0 or 1"); return MQ_ERR_ARG; }
     if (pk->n_events < 1 || pk->n_picks < 1 || pk->n_stations < 1) { set_error("mq_create: empty pick set"); return MQ_ERR_ARG; }
     if (cfg->max_dim < 1) { set_error("mq_create: max_dim < 1"); return MQ_ERR_ARG; }
     *out = nullptr;

@@ -20,6 +20,7 @@
 #include "forward.cuh"
 #include "launch_count.h"
 #include "state.h"
+#include "tria.cuh"
 
 namespace mq {
 
@@ -219,9 +220,19 @@ __global__ void init_chains_kernel(SamplerParams p, Handle hd, SamplerDev s)
                                                                 1.0f, (float)p.nz, &ok);
         else dim = 1;
         if (dim < 1) dim = 1;
+        int first = 0;
+        if (g.tria == 1) {   // two fixed nuclei at the top and the bottom of the model (src/mcmc_eq.c:577-588)
+            dim += 2; first = 2;
+            z[0] = p.zmin; z[1] = p.zmax;
+            for (int i = 0; i < 2; i++) {
+                const float value = g.start_vp + (z[i] - g.grid.z0) * g.start_vp_grad;
+                vp[i] = value + rng.gauss_bounded(value, g.sdev_start_vp, g.vpmin, g.vpmax, &ok);
+                vpvs[i] = g.start_vpvs + rng.gauss_bounded(g.start_vpvs, g.sdev_start_vpvs, g.vpvsmin, g.vpvsmax, &ok);
+            }
+        }
         if (dim > p.md) dim = p.md;
-        for (int i = 0; i < dim; i++) z[i] = rng.between(p.zmin, p.zmax);
-        for (int i = 0; i < dim; i++) {
+        for (int i = first; i < dim; i++) z[i] = rng.between(p.zmin, p.zmax);
+        for (int i = first; i < dim; i++) {
             const float value = g.start_vp + (z[i] - g.grid.z0) * g.start_vp_grad;
             vp[i] = value + rng.gauss_bounded(value, g.sdev_start_vp, g.vpmin, g.vpmax, &ok);
             vpvs[i] = g.start_vpvs + rng.gauss_bounded(g.start_vpvs, g.sdev_start_vpvs, g.vpvsmin, g.vpvsmax, &ok);
@@ -327,11 +338,13 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
         break;
     }
     case 'P': case 'V': case 'M': {
-        if (kind == 'M' && !(dim > 1)) { s.not_valid[c] = 1; break; }
+        // the two end nuclei of a linear-gradient model are never moved (src/mcmc_eq.c:990-998)
+        const int fixed = (g.tria == 1) ? 2 : 0;
+        if (kind == 'M' && !(dim > 1 + fixed)) { s.not_valid[c] = 1; break; }
         int t;
         for (t = 0; t < kMaxTries; t++) {
             for (int i = 0; i < dim; i++) { nz_[i] = z[i]; nvp[i] = vp[i]; nvpvs[i] = vpvs[i]; }
-            const int idx = rng.below(dim);
+            const int idx = (kind == 'M') ? fixed + rng.below(dim - fixed) : rng.below(dim);
             if (kind == 'P') nvp[idx] = vp[idx] + rng.gauss_bounded(vp[idx], g.sdevvp, g.vpmin, g.vpmax, &ok);
             else if (kind == 'V') nvpvs[idx] = vpvs[idx] + rng.gauss_bounded(vpvs[idx], g.sdevvpvs, g.vpvsmin, g.vpvsmax, &ok);
             else nz_[idx] = z[idx] + rng.gauss_bounded(z[idx], g.sdevz, p.zmin, p.zmax, &ok);
@@ -369,11 +382,12 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
         break;
     }
     case 'D': {
-        if (!(dim > 1)) { s.not_valid[c] = 1; break; }
+        const int fixed = (g.tria == 1) ? 2 : 0;   // ... nor removed (src/mcmc_eq.c:1059-1067)
+        if (!(dim > 1 + fixed)) { s.not_valid[c] = 1; break; }
         int t;
         double lf = 0.0;
         for (t = 0; t < kMaxTries; t++) {
-            const int dead = rng.below(dim);
+            const int dead = fixed + rng.below(dim - fixed);
             const int nb = find_neighbor_dev(z, dim, dead);
             const float dv = vp[dead] - vp[nb], ds = vpvs[dead] - vpvs[nb];
             lf = log((double)((g.vpmax - g.vpmin) / g.sdevvp) / sqrt(2.0 * MQ_PI)) -
@@ -611,16 +625,24 @@ __device__ void posterior_accumulate(const SamplerParams& p, const Handle& hd, i
     const mq_config& g = p.cfg;
     for (int i = threadIdx.x; i < p.nz; i += blockDim.x) {
         const float zz = __fadd_rn(__fmul_rn((float)i, g.grid.h), g.grid.z0);
-        const int k = find_in_cell_dev(z, dim, zz);
-        float vv = vp[k];
-        const float vvx = vp[find_in_cell_dev(z, dim, __fsub_rn(zz, g.grid.h))];
-        if (vv != vvx) atomicAdd(&boundary[i], 1);
+        float vv, rr;
+        if (g.tria == 1) {   // interpolated profile, no layer boundaries (src/analyse_eq.c:573-580,593-598)
+            int lo, hi;
+            tria::segment_of_node(z, dim, i, g.grid.h, g.grid.z0, &lo, &hi);
+            vv = tria::line_through(zz, z[lo], vp[lo], z[hi], vp[hi]);
+            rr = tria::line_through(zz, z[lo], vpvs[lo], z[hi], vpvs[hi]);
+        } else {
+            const int k = find_in_cell_dev(z, dim, zz);
+            vv = vp[k];
+            rr = vpvs[k];
+            const float vvx = vp[find_in_cell_dev(z, dim, __fsub_rn(zz, g.grid.h))];
+            if (vv != vvx) atomicAdd(&boundary[i], 1);
+        }
         if (vv > g.vpmax) vv = g.vpmax;
         if (vv < g.vpmin) vv = g.vpmin;
         int j = (int)__fdiv_rn(__fsub_rn(vv, g.vpmin), P.dv);
         if (j > P.ndv - 1) j = P.ndv - 1;
         atomicAdd(&hist_vp[(size_t)j * p.nz + i], 1);
-        float rr = vpvs[k];
         if (rr > g.vpvsmax) rr = g.vpvsmax;
         if (rr < g.vpvsmin) rr = g.vpvsmin;
         j = (int)__fdiv_rn(__fsub_rn(rr, g.vpvsmin), P.dvpvs);

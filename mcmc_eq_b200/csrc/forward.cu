@@ -6,6 +6,7 @@
 #include "forward.cuh"
 #include "eikonal.cuh"
 #include "launch_count.h"
+#include "tria.cuh"
 
 #include <vector>
 
@@ -40,7 +41,8 @@ cudaError_t launch_build_items_all(Handle* h, const EvalView& v, int calct)
 // ---- Voronoi rasteriser -------------------------------------------------------------------
 // One thread per (item, depth node).  Nearest nucleus in depth, ties -> highest index
 // (find_in_cell, src/mod_grd.c:93-110); vs = vp/vpvs; slow = h/v (src/misfit.c:209-213,263).
-__global__ void rasterise_kernel(int nz, int md, int n, float hgrid, float z0, const int32_t* n_items,
+// tria != 0: linear interpolation between the depth-sorted nuclei instead (src/misfit.c:217-250, tria.cuh).
+__global__ void rasterise_kernel(int nz, int md, int n, float hgrid, float z0, int tria, const int32_t* n_items,
                                  const int32_t* item_chain, const int32_t* item_phase, const int32_t* mbuf,
                                  const int32_t* dim, const float* z, const float* vp, const float* vpvs, float* slow)
 {
@@ -51,6 +53,16 @@ __global__ void rasterise_kernel(int nz, int md, int n, float hgrid, float z0, c
     const int b = mbuf[c];
     const size_t mo = ((size_t)b * n + c) * md;
     const int d = dim[b * n + c];
+    if (tria) {
+        int lo, hi;
+        tria::segment_of_node(z + mo, d, iz, hgrid, z0, &lo, &hi);
+        const float zq = __fadd_rn(z0, __fmul_rn((float)iz, hgrid));
+        const bool isS = item_phase[item] != 0;
+        const float v0 = isS ? __fdiv_rn(vp[mo + lo], vpvs[mo + lo]) : vp[mo + lo];
+        const float v1 = isS ? __fdiv_rn(vp[mo + hi], vpvs[mo + hi]) : vp[mo + hi];
+        slow[(size_t)item * nz + iz] = __fdiv_rn(hgrid, tria::line_through(zq, z[mo + lo], v0, z[mo + hi], v1));
+        return;
+    }
     const float zq = __fadd_rn(z0, __fmul_rn((float)iz, hgrid));
     float best = 3.402823466e+38f;
     int k = 0;
@@ -68,7 +80,7 @@ cudaError_t launch_rasterise(Handle* h, const EvalView& v, int max_items)
 {
     const int threads = max_items * h->nz;
     if (threads <= 0) return cudaSuccess;
-    rasterise_kernel<<<(threads + 127) / 128, 128, 0, h->stream>>>(h->nz, h->md, h->n, h->cfg.grid.h, h->cfg.grid.z0,
+    rasterise_kernel<<<(threads + 127) / 128, 128, 0, h->stream>>>(h->nz, h->md, h->n, h->cfg.grid.h, h->cfg.grid.z0, h->cfg.tria,
                                                                     h->n_items, h->item_chain, h->item_phase, v.mbuf, h->dim,
                                                                     h->z, h->vp, h->vpvs, h->slow);
     count_launch();

@@ -157,7 +157,6 @@ int main(int argc, char** argv)
     if (mqio_read_config(argv[1], &cfg) != MQ_OK) FAIL("%s", mqio_last_error());
     if (mqio_read_picks(argv[3], &pk) != MQ_OK) FAIL("%s", mqio_last_error());
     if (mqio_check_picks(&cfg, &pk, quiet ? NULL : stderr) != MQ_OK) FAIL("%s", mqio_last_error());
-    if (cfg.tria != 0) FAIL("config line 29: only the Voronoi parameterisation (0) is implemented");
     if (cfg.aflag == 3) { from_file = 1; cfg.aflag = 0; }      /* src/mcmc_eq.c:381 */
 
     {

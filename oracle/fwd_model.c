@@ -59,6 +59,37 @@ void fm_rasterise(const fm_grid *g, int dim, const float *z, const float *vp, co
     }
 }
 
+/* TRIA = 1 (config line 29): linear interpolation between the depth-sorted nuclei, src/misfit.c:217-250.  The sort is a
+ * stable one (the reference's bubble sort swaps on strict > only); the segment index of a depth that no segment holds
+ * is the one of the previous depth node (the reference's k is not reset inside the depth loop, :233). */
+void fm_rasterise_tria(const fm_grid *g, int dim, const float *z, const float *vp, const float *vpvs, int ps, float *slow)
+{
+    float *zs = (float *)malloc(3 * (size_t)(dim > 0 ? dim : 1) * sizeof(float));
+    float *ps_ = zs + dim, *rs = ps_ + dim;
+    int i, j, iz, k = 0;
+    for (i = 0; i < dim; i++) {           /* insertion sort, stable */
+        const float kz = z[i], kp = vp[i], kr = vpvs[i];
+        for (j = i - 1; j >= 0 && zs[j] > kz; j--) { zs[j + 1] = zs[j]; ps_[j + 1] = ps_[j]; rs[j + 1] = rs[j]; }
+        zs[j + 1] = kz; ps_[j + 1] = kp; rs[j + 1] = kr;
+    }
+    for (iz = 0; iz < g->nz; iz++) {
+        const float zq = g->z0 + (float)iz * g->h;
+        float a, b, v;
+        for (i = 0; i < dim - 1; i++)
+            if (zq >= zs[i] && zq < zs[i + 1]) k = i;
+        if (ps == 1) {
+            a = (ps_[k + 1] - ps_[k]) / (zs[k + 1] - zs[k]);
+            b = ps_[k] - a * zs[k];
+        } else {
+            a = (ps_[k + 1] / rs[k + 1] - ps_[k] / rs[k]) / (zs[k + 1] - zs[k]);
+            b = ps_[k] / rs[k] - a * zs[k];
+        }
+        v = a * zq + b;
+        slow[iz] = g->h / v;
+    }
+    free(zs);
+}
+
 int fm_build_table(const fm_grid *g, const float *slow, float *ttt)
 {
     const int nxmod = fm_nxmod(g), nz = g->nz;

@@ -30,6 +30,7 @@ float fm_dst(float x1, float x2, float y1, float y2);                  /* src/mc
 void fm_receiver(const fm_grid *g, float z, int *layer, float *w1, float *w2);
 /* slow[iz] = h / v(z0 + iz*h), ps = 1 (P) or 2 (S); src/misfit.c:205-214, 256-266 */
 void fm_rasterise(const fm_grid *g, int dim, const float *z, const float *vp, const float *vpvs, int ps, float *slow);
+void fm_rasterise_tria(const fm_grid *g, int dim, const float *z, const float *vp, const float *vpvs, int ps, float *slow);
 /* ttt[(j*nz + iz)*nxmod + i] = time at distance node i, receiver row j, source row iz; src/misfit.c:270-289 */
 int fm_build_table(const fm_grid *g, const float *slow, float *ttt);
 /* bilinear lookup in one receiver layer (ttt_layer = &ttt[j*nz*nxmod]); src/interpol.c:43-83 */

@@ -34,7 +34,7 @@ def oracle_forward(cfg, pk, z, vp, vpvs, eq, pres, sres, want_tables=False):
     tabs = []
     for ps in (1, 2):
         slow = np.zeros(nz, np.float32)
-        L.fm_rasterise(C.byref(g), dim, ptr(z), ptr(vp), ptr(vpvs), ps, ptr(slow))
+        (L.fm_rasterise_tria if cfg.tria == 1 else L.fm_rasterise)(C.byref(g), dim, ptr(z), ptr(vp), ptr(vpvs), ps, ptr(slow))
         t = np.zeros((nz, nz, nxmod), np.float32)
         rc = L.fm_build_table(C.byref(g), ptr(slow), ptr(t))
         assert rc == 0
@@ -71,6 +71,21 @@ def random_states(rng, cfg, pk, n, kind="posterior", max_layers=20):
         sres = rng.normal(0, 0.3, pk.n_stations).astype(np.float32)
         noise = rng.uniform(0.05, 1.0, 8).astype(np.float32)
         out.append(dict(z=z, vp=vp, vpvs=vpvs, eq=eq, pres=pres, sres=sres, noise=noise))
+    return out
+
+
+def tria_states(rng, cfg, pk, n, max_layers=12):
+    """Random chain states of the linear-gradient parameterisation (config line 29 = 1): nuclei 0 and 1 sit at the top
+    and the bottom of the model (src/mcmc_eq.c:577-588), velocities increase with depth plus scatter."""
+    g = cfg.grid
+    zmin, zmax = g.z0, g.z0 + (g.nz - 1) * g.h
+    out = random_states(rng, cfg, pk, n, "posterior", max_layers)
+    for s in out:
+        nl = len(s["z"]) + 2
+        z = np.concatenate([[zmin, zmax], s["z"]]).astype(np.float32)
+        vp = (4.5 + 0.04 * (z - zmin) + rng.normal(0, 0.25, nl)).astype(np.float32)
+        vpvs = (1.73 + rng.normal(0, 0.05, nl)).astype(np.float32)
+        s.update(z=z, vp=vp, vpvs=vpvs)
     return out
 
 

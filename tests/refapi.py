@@ -80,7 +80,8 @@ class RefForward:
         self.nos = 1 + max(max([d.p_picks[j].st_id for j in range(d.nobs_p)] + [d.s_picks[j].st_id for j in range(d.nobs_s)])
                            for d in self.data[: self.ne])
 
-    def forward(self, z, vp, vpvs, eq, pres, sres, calct=3, eikonal=1):
+    def forward(self, z, vp, vpvs, eq, pres, sres, calct=3, eikonal=1, tria=0):
+        C.c_int.in_dll(self.ref, "TRIA").value = tria
         m = Model()
         m.dimension, m.noq, m.nos = len(z), self.ne, self.nos
         for i in range(len(z)):

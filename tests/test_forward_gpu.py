@@ -43,6 +43,26 @@ def test_forward_matches_reference_fixtures(name):
     smp.close()
 
 
+def test_tria_forward_matches_reference_fixtures(oracle):
+    """Config line 29 = 1 (linear gradients between the nuclei, src/misfit.c:217-250) against cal_fit_newx of the compiled
+    reference with TRIA = 1 (tests/golden/forward_ref_tria.npz) and per pick against the oracle."""
+    d = np.load(os.path.join(util.GOLDEN, "forward_ref_tria.npz"))
+    n = int(d["n"])
+    mq, cfg, pk, smp = _setup("example2", n, tria=1)
+    states = [{k: d[f"{i}_{k}"] for k in ("z", "vp", "vpvs", "eq", "pres", "sres", "noise")} for i in range(n)]
+    mf, origin = smp.forward_host(fh.fill_models(smp.new_models(32), states), 3)
+    for i, s in enumerate(states):
+        _check_sums(mf[i], d[f"{i}_mf"])
+        assert np.abs(origin[i] - d[f"{i}_origin"]).max() < 1e-4
+        _rmf, _rorg, rres, rtp = fh.oracle_forward(cfg, pk, s["z"], s["vp"], s["vpvs"], s["eq"], s["pres"], s["sres"])
+        res, tp = smp.predictions(i)
+        assert np.abs(tp - rtp).max() < 1e-4 and np.abs(res - rres).max() < 1e-4
+    for ps, key in ((1, "0_tabP_rows12"), (2, "0_tabS_rows12")):
+        tab = smp.table(0, ps)
+        assert (np.abs(tab[1:3] - d[key]) <= util.eikonal_tol(d[key])).all()
+    smp.close()
+
+
 def test_forward_matches_oracle_per_pick(oracle):
     mq, cfg, pk, smp = _setup("example2", 6)
     rng = np.random.default_rng(21)

@@ -156,3 +156,54 @@ def test_chain_oracle_reproduces_every_recorded_decision(oracle):
             assert np.array_equal(mf, log["mf"][i]), (i, kind)
             assert np.array_equal(origin, prop["origin"])
     assert set(kinds) == set("QRPVMBDN"), kinds     # every arm of the proposal switch occurs in the recorded chain
+
+
+# ---- the linear-gradient parameterisation (config line 29 = 1) ---------------------------------------------------------
+def test_tria_forward_oracle_matches_golden_bitwise(oracle):
+    """fm_rasterise_tria (src/misfit.c:217-250) + tables + residual loop == cal_fit_newx of the compiled reference with
+    TRIA = 1 (tests/golden/forward_ref_tria.npz): states with nuclei at equal depths and with the two end nuclei only."""
+    import tempfile
+    import mcmc_eq_b200 as mq
+    from tests import fwd_helpers as fh
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, tria=1)
+        cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
+    assert cfg.tria == 1
+    d = np.load(os.path.join(util.GOLDEN, "forward_ref_tria.npz"))
+    for i in range(int(d["n"])):
+        s = {k: d[f"{i}_{k}"] for k in ("z", "vp", "vpvs", "eq", "pres", "sres")}
+        mf, origin, _r, _t, tabs = fh.oracle_forward(cfg, pk, s["z"], s["vp"], s["vpvs"], s["eq"], s["pres"], s["sres"], True)
+        assert np.array_equal(mf.view(np.uint32), d[f"{i}_mf"].view(np.uint32)), (i, mf, d[f"{i}_mf"])
+        assert np.array_equal(origin.view(np.uint32), d[f"{i}_origin"].view(np.uint32))
+        if i == 0:
+            assert np.array_equal(tabs[0][1:3], d["0_tabP_rows12"]) and np.array_equal(tabs[1][1:3], d["0_tabS_rows12"])
+
+
+def test_tria_chain_oracle_reproduces_every_recorded_decision(oracle):
+    """The recorded TRIA = 1 chain of the unmodified reference (tests/golden/replay_example2_tria.npz): decisions from
+    oracle/chain.c for every proposal, class sums from the oracle's forward for a sample; the two end nuclei are never
+    moved or removed (src/mcmc_eq.c:990-998,1059-1067)."""
+    import tempfile
+    import mcmc_eq_b200 as mq
+    from tests import replay, fwd_helpers as fh
+    log = replay.load("example2_tria")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=78, tria=1)
+        cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
+    g = cfg.grid
+    zmin, zmax = np.float32(g.z0), np.float32(g.z0 + (g.nz - 1) * g.h)
+    old_ll = replay.loglik(log["mf"][0], log["noise"][0])
+    kinds = {}
+    for i, kind, q, lf, u, acc, cur, prop in replay.proposals(log, cfg, pk.n_class):
+        kinds[kind] = kinds.get(kind, 0) + 1
+        assert prop["dim"] >= 2 and prop["z"][0] == zmin and prop["z"][1] == zmax, (i, kind)
+        new_ll = replay.loglik(log["mf"][i], prop["noise"])
+        alpha = oracle.ch_alpha(lf, new_ll, old_ll)
+        assert (u < alpha) == acc, (i, kind, u, alpha, acc)
+        if acc:
+            old_ll = new_ll
+        if i % 40 == 1 or kind in "BDM":
+            mf, origin, _r, _t = fh.oracle_forward(cfg, pk, prop["z"], prop["vp"], prop["vpvs"], prop["eq"], prop["pres"], prop["sres"])
+            assert np.array_equal(mf, log["mf"][i]), (i, kind)
+            assert np.array_equal(origin, prop["origin"])
+    assert set(kinds) >= set("QRPVBN"), kinds

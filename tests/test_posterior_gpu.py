@@ -18,11 +18,29 @@ def _nearest(z, zq):
     return len(z) - 1 - int(np.argmin(d2[::-1]))          # ties -> highest index (src/mod_grd.c:93-110)
 
 
-def test_posterior_matches_numpy_and_analyse_eq():
+def _tria_profile(z, v, nz, h, z0):
+    """Linear interpolation between the depth-sorted nuclei in the reference's float arithmetic; a depth node that no
+    segment holds keeps the segment of the node above (src/analyse_eq.c:573-580)."""
+    order = np.argsort(z, kind="stable")
+    zs, vs = z[order].astype(np.float32), v[order].astype(np.float32)
+    out, k = np.zeros(nz, np.float32), 0
+    for i in range(nz):
+        zz = np.float32(np.float32(i) * np.float32(h) + np.float32(z0))
+        for si in range(len(zs) - 1):
+            if zs[si] <= zz < zs[si + 1]:
+                k = si
+        a = np.float32(np.float32(vs[k + 1] - vs[k]) / np.float32(zs[k + 1] - zs[k]))
+        b = np.float32(vs[k] - np.float32(a * zs[k]))
+        out[i] = np.float32(np.float32(a * zz) + b)
+    return out
+
+
+@pytest.mark.parametrize("tria", [0, 1])
+def test_posterior_matches_numpy_and_analyse_eq(tria):
     import mcmc_eq_b200 as mq
     from mcmc_eq_b200.io import format_record
     d = tempfile.mkdtemp(prefix="mqp_")
-    cfgp, pkp = inputs.materialise("example2", d, j_max_start=40, j_max_main=160, deci=10, true_random=5)
+    cfgp, pkp = inputs.materialise("example2", d, j_max_start=40, j_max_main=160, deci=10, true_random=5, tria=tria)
     cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
     n, burn, dv, dvs = 6, 50, np.float32(0.1), np.float32(0.02)
     smp = mq.Sampler(cfg, pk, n, 0, 5)
@@ -44,14 +62,20 @@ def test_posterior_matches_numpy_and_analyse_eq():
     hp, hs, bd = np.zeros((dims.ndv, g.nz), np.int32), np.zeros((dims.ndvpvs, g.nz), np.int32), np.zeros(g.nz, np.int32)
     vsum = np.zeros((g.nz, 4))
     for r in used:
+        if tria:
+            assert r["z"][0] == np.float32(g.z0) and r["z"][1] == np.float32(g.z0 + (g.nz - 1) * g.h)
+            pv, pr = _tria_profile(r["z"], r["vp"], g.nz, g.h, g.z0), _tria_profile(r["z"], r["vpvs"], g.nz, g.h, g.z0)
         for i in range(g.nz):
             zz = np.float32(np.float32(i) * np.float32(g.h) + np.float32(g.z0))
-            k = _nearest(r["z"], zz)
-            vv = np.float32(r["vp"][k])
-            bd[i] += vv != np.float32(r["vp"][_nearest(r["z"], np.float32(zz - np.float32(g.h)))])
+            if tria:
+                vv, rr0 = pv[i], pr[i]
+            else:
+                k = _nearest(r["z"], zz)
+                vv, rr0 = np.float32(r["vp"][k]), np.float32(r["vpvs"][k])
+                bd[i] += vv != np.float32(r["vp"][_nearest(r["z"], np.float32(zz - np.float32(g.h)))])
             vv = min(max(vv, np.float32(cfg.vpmin)), np.float32(cfg.vpmax))
             hp[int(np.float32(vv - np.float32(cfg.vpmin)) / dv), i] += 1
-            rr = min(max(np.float32(r["vpvs"][k]), np.float32(cfg.vpvsmin)), np.float32(cfg.vpvsmax))
+            rr = min(max(rr0, np.float32(cfg.vpvsmin)), np.float32(cfg.vpvsmax))
             hs[int(np.float32(rr - np.float32(cfg.vpvsmin)) / dvs), i] += 1
             vsum[i] += [float(vv), float(vv) ** 2, float(rr), float(rr) ** 2]
     assert np.array_equal(post["hist_vp"], hp) and np.array_equal(post["hist_vpvs"], hs) and np.array_equal(post["boundary"], bd)

@@ -28,11 +28,17 @@ def _models_from(smp, st, n):
     return m
 
 
-def test_replayed_reference_chain_makes_the_reference_decisions():
+# (fixture, chain seed, config line 29, evaluated proposals, accepted, rejected): the second chain runs the linear-gradient
+# parameterisation (TRIA = 1)
+CHAINS = [("example2", 77, 0, 312, 200, 112), ("example2_tria", 78, 1, 343, 200, 143)]
+
+
+@pytest.mark.parametrize("fixture,seed,tria,n_props,n_acc,n_rej", CHAINS)
+def test_replayed_reference_chain_makes_the_reference_decisions(fixture, seed, tria, n_props, n_acc, n_rej):
     import mcmc_eq_b200 as mq
-    log = replay.load("example2")
+    log = replay.load(fixture)
     with tempfile.TemporaryDirectory() as d:
-        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=77)
+        cfgp, pkp = inputs.materialise("example2", d, j_max_start=60, j_max_main=140, deci=20, true_random=seed, tria=tria)
         cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
     n = 3                                                     # three copies of the chain: results must be identical
     smp = mq.Sampler(cfg, pk, n, 0, 1)
@@ -63,7 +69,7 @@ def test_replayed_reference_chain_makes_the_reference_decisions():
             smp.forward(3)
         if acc:
             old_ll_ref = new_ll_ref
-    assert n_eval == 312 and kinds_seen == set("QRPVMBDN")
+    assert n_eval == n_props and kinds_seen == set("QRPVMBDN")
     assert n_match + n_tie == n_eval and n_tie <= 6, (n_match, n_tie)
     assert worst_ll < 2e-5
     # the replayed chain ends in the reference's final state with the reference's bookkeeping
@@ -73,6 +79,6 @@ def test_replayed_reference_chain_makes_the_reference_decisions():
     assert m.dim[0] == last["dim"] and np.array_equal(m.z[0, :last["dim"]], last["z"]) and np.array_equal(m.eq[0], last["eq"])
     assert np.array_equal(m.pres[0], last["pres"]) and np.array_equal(m.noise[0], last["noise"])
     if n_tie == 0:
-        assert counts[0, 17] == 200 and counts[0, 18] == 112 and counts[0, 0] == 312
+        assert counts[0, 17] == n_acc and counts[0, 18] == n_rej and counts[0, 0] == n_props
     print(f"replay: {n_match}/{n_eval} decisions identical, {n_tie} declared near-ties, worst |dll|/|ll| = {worst_ll:.2e}")
     smp.close()

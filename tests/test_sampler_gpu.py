@@ -103,3 +103,25 @@ def test_same_seed_same_chains():
     rb = b.stats()
     assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
     a.close(); b.close()
+
+
+def test_linear_gradient_models_keep_their_end_nuclei():
+    """Config line 29 = 1: start models carry two extra nuclei at the top and the bottom of the model
+    (src/mcmc_eq.c:577-588) which the move and death arms never touch (:990-998, :1059-1067); the maintained
+    likelihood still equals a from-scratch forward."""
+    mq, cfg, pk, smp = _sampler("example2", 32, seed=13, j_max_start=0, j_max_main=100000, tria=1)
+    g = cfg.grid
+    zmin, zmax = np.float32(g.z0), np.float32(g.z0 + (g.nz - 1) * g.h)
+    smp.init_chains()
+    m = smp.get_models()
+    assert (m.dim >= 3).all() and (m.z[:, 0] == zmin).all() and (m.z[:, 1] == zmax).all()
+    smp.step(80, "QVRPBDMN")
+    counts, ll, rms = smp.stats()
+    tried = counts[:, 1:17].reshape(32, 8, 2).sum((0, 2))
+    assert (tried > 0).all() and counts[:, 17].sum() > 0
+    m = smp.get_models()
+    assert (m.dim >= 2).all() and (m.z[:, 0] == zmin).all() and (m.z[:, 1] == zmax).all()
+    _mf, _ = smp.forward(3)
+    _c, ll2, rms2 = smp.stats()
+    assert np.allclose(ll2, ll, rtol=2e-5, atol=1e-3) and np.allclose(rms2, rms, rtol=1e-5)
+    smp.close()

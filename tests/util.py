@@ -52,6 +52,7 @@ def oracle() -> C.CDLL:
         L.fm_dst.restype = C.c_float
         L.fm_receiver.argtypes = [C.POINTER(FmGrid), C.c_float, ip, fp, fp]
         L.fm_rasterise.argtypes = [C.POINTER(FmGrid), C.c_int, fp, fp, fp, C.c_int, fp]
+        L.fm_rasterise_tria.argtypes = [C.POINTER(FmGrid), C.c_int, fp, fp, fp, C.c_int, fp]
         L.fm_build_table.argtypes = [C.POINTER(FmGrid), fp, fp]
         L.fm_traveltime.argtypes = [fp, C.POINTER(FmGrid), C.c_float, C.c_float]
         L.fm_traveltime.restype = C.c_float

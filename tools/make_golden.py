@@ -314,8 +314,57 @@ def ensemble_ref(n_chains=32):
     print("ensemble_ref:", n_chains, "chains; final rms", np.mean([o["rms"][-1] for o in out]), "+-", np.std([o["rms"][-1] for o in out]))
 
 
+TRIA_CHAIN = dict(j_max_start=60, j_max_main=140, deci=20, true_random=78, tria=1)
+
+
+def tria_ref():
+    """The linear-gradient parameterisation (config line 29 = 1) of the compiled reference: cal_fit_newx on seeded states
+    (forward_ref_tria.npz) and a short fixed-seed chain with its proposal stream (chain_ref_example2_tria.out,
+    replay_example2_tria.npz)."""
+    from tests import fwd_helpers as fh
+    ref = util.reflib()
+    cfgp, pkp = os.path.join(REF, "Example2", "config_eqx.dat"), os.path.join(REF, "Example2", "picks.mcmc")
+    c = mq.read_config(cfgp)
+    pk = mq.Picks.read(pkp)
+    g = dict(h=c.grid.h, nx=c.grid.nx, ny=c.grid.ny, nz=c.grid.nz, x0=c.grid.x0, y0=c.grid.y0, z0=c.grid.z0)
+    rf = refapi.RefForward(ref, g, pkp)
+    rng = np.random.default_rng(29)
+    states = fh.tria_states(rng, c, pk, 3)
+    # one state with two nuclei at the same depth and one with only the two end nuclei
+    states[1]["z"][3] = states[1]["z"][2]
+    states[2] = {k: (v[:2].copy() if k in ("z", "vp", "vpvs") else v) for k, v in states[2].items()}
+    out = {"n": np.array(len(states))}
+    for i, s in enumerate(states):
+        mf, org = rf.forward(s["z"], s["vp"], s["vpvs"], s["eq"], s["pres"], s["sres"], 3, 1, tria=1)
+        for k, v in s.items():
+            out[f"{i}_{k}"] = v
+        out[f"{i}_mf"] = mf
+        out[f"{i}_origin"] = org
+        if i == 0:
+            out["0_tabP_rows12"] = rf.table(1)[1:3]
+            out["0_tabS_rows12"] = rf.table(2)[1:3]
+    C.c_int.in_dll(ref, "TRIA").value = 0
+    np.savez_compressed(os.path.join(G, "forward_ref_tria.npz"), **out)
+    exe, rexe = os.path.join(util.REF_DIR, "mcmc_eq"), os.path.join(util.REF_DIR, "replay_log")
+    with tempfile.TemporaryDirectory() as d:
+        cfgp, pkp = inputs.materialise("example2", d, **TRIA_CHAIN)
+        outp, logp = os.path.join(d, "rjx-000.out"), os.path.join(d, "log.bin")
+        subprocess.run([exe, cfgp, outp, pkp], check=True, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        txt = open(outp).read()
+        subprocess.run([rexe, logp, cfgp, outp, pkp], check=True, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert open(outp).read() == txt
+        log = read_replay_log(logp)
+    open(os.path.join(G, "chain_ref_example2_tria.out"), "w").write(txt)
+    np.savez_compressed(os.path.join(G, "replay_example2_tria.npz"), **log)
+    print("tria_ref:", len(states), "states;", len(log["u"]), "records,", int(log["accepted"][1:].sum()), "accepted")
+
+
 if __name__ == "__main__":
     os.makedirs(G, exist_ok=True)
+    if len(sys.argv) > 1:        # only the named fixtures, e.g. `python tools/make_golden.py tria_ref`
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     inputs_of("example", os.path.join(REF, "Example/config_eqx.dat"), os.path.join(REF, "Example/picks_synth"))
     inputs_of("example2", os.path.join(REF, "Example2/config_eqx.dat"), os.path.join(REF, "Example2/picks.mcmc"))
     eikonal_fields()
@@ -325,4 +374,5 @@ if __name__ == "__main__":
     fw_mod_ref()
     fw_ref()
     ensemble_ref()
+    tria_ref()
     print(subprocess.run(["du", "-sh", G], capture_output=True, text=True).stdout)
