@@ -51,11 +51,27 @@ def kernel_traffic(kernel, solves_per_launch):
     return float(t["dram_bytes_per_launch"]) * solves_per_launch / float(t["solves_per_launch"])
 
 
+def kernel_instructions(kernel, solves_per_launch):
+    """Warp instructions per launch of the dominant kernel (smsp__inst_executed.sum of the same ncu capture), scaled."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(kernel)
+    if not t or "warp_instructions_per_launch" not in t:
+        return None
+    return float(t["warp_instructions_per_launch"]) * solves_per_launch / float(t["solves_per_launch"])
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def torch_sm_count(device):
+    import torch
+    return torch.cuda.get_device_properties(device).multi_processor_count
 
 
 class ClockSampler:
@@ -343,6 +359,14 @@ def main():
                     "layout": "receiver rows only are stored (3 of 62 rows); algorithmic bytes count the full field as the reference materialises it",
                     "smem": {"achieved": smem_alg, "peak": SMEM_PEAK_GBS, "unit": "GB/s", "frac": smem_alg / SMEM_PEAK_GBS,
                              "algorithmic_bytes_per_node_update": 32}}
+        # what actually binds the kernel (profiles/README.md): warp-instruction issue, 4 schedulers per SM, 1 per clock
+        winst = kernel_instructions(kernel, solves_per_launch)
+        if winst:
+            sm_ghz = float(clk.get("sm_mhz") or 1965.0) / 1000.0
+            issue_peak = torch_sm_count(device) * 4 * sm_ghz
+            roofline["issue"] = {"achieved": winst / t_launch / 1e9, "peak": issue_peak, "unit": "G warp-instructions/s",
+                                 "frac": winst / t_launch / 1e9 / issue_peak, "warp_instructions_per_launch": winst,
+                                 "source": "smsp__inst_executed.sum of the committed ncu capture (profiles/traffic.json)"}
 
     # ---- end to end through the plugin call with host buffers ----------------------------------------------
     import torch

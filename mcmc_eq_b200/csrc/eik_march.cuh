@@ -76,30 +76,23 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // value of a sentinel node (k < 0 or k > ke): above every travel time, strictly increasing with k
 __device__ __forceinline__ float sentinel(int k, int ke) { return k < 0 ? kEdge : kEdge * (1.0f + (float)(k - ke) * (1.0f / 1024.0f)); }
 
-// One column: past column in TMEM array tp, new column into array tc (column addresses of this warp's lane quarter).
-// Slowness cells: either in shared memory (S: cell k at S[k*32], S[-2..-1] = S[ke..] = INF) or, with S_TMEM, in a third
-// TMEM array tS (cell k at column k+1, cells -1 and ke.. = INF).
+// One column: past column in TMEM array tp, new column into array tc, slowness cells in array tS (cell k at column k+1,
+// cells -1 and ke.. = INF); all three are column addresses of this warp's lane quarter.
 // MASKED: lanes with need == false keep their past column (their box phase ended at a later column than the others').
-template <int NB, bool MASKED, bool S_TMEM>
-__device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, const float* S, uint32_t tS)
+template <int NB, bool MASKED>
+__device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, uint32_t tS)
 {
-    constexpr int CA = 4 * NB;
     bool tie = false;
     float pa_cur[4], pb_cur[4], sa_cur[4], sb_cur[4];
     tmem_ld4(tp, pa_cur);
     tmem_ld4(tp + 4 * (NB - 1), pb_cur);
-    if (S_TMEM) { tmem_ld4(tS, sa_cur); tmem_ld4(tS + 4 * (NB - 1), sb_cur); }
-    else {
-#pragma unroll
-        for (int c = 0; c < 4; c++) { sa_cur[c] = 0.f; sb_cur[c] = 0.f; }
-    }
+    tmem_ld4(tS, sa_cur);
+    tmem_ld4(tS + 4 * (NB - 1), sb_cur);
     tmem_wait_ld(pa_cur, pb_cur);
     tmem_wait_ld(sa_cur, sb_cur);
     // chain A starts at node -1 (parent -2: nothing there), chain B at node CA-2 (parent CA-1: nothing there)
     eikf::ChainA a{2.0f * kEdge, pa_cur[0], kInf, kInf};
     eikf::ChainB b{4.0f * kEdge, pb_cur[3], kInf, kInf};
-    const float* sa = S - 32;                    // &S[ka], ka = -1
-    const float* sb = S + (long)(CA - 3) * 32;   // &S[kb - 1], kb = CA-2
 
 #pragma unroll 1
     for (int j = 0; j < NB; j++) {
@@ -108,14 +101,10 @@ __device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, 
         if (j == NB / 2) tmem_wait_st();         // its stores must have landed before they are read back
         if (j + 1 < NB) {
             tmem_ld4(tp + 4 * (j + 1), pa_nxt); tmem_ld4(tp + 4 * (NB - 2 - j), pb_nxt);
-            if (S_TMEM) { tmem_ld4(tS + 4 * (j + 1), sa_nxt); tmem_ld4(tS + 4 * (NB - 2 - j), sb_nxt); }
+            tmem_ld4(tS + 4 * (j + 1), sa_nxt); tmem_ld4(tS + 4 * (NB - 2 - j), sb_nxt);
         } else {
 #pragma unroll
             for (int c = 0; c < 4; c++) { pa_nxt[c] = 4.0f * kEdge; pb_nxt[c] = 2.0f * kEdge; sa_nxt[c] = kInf; sb_nxt[c] = kInf; }
-        }
-        if (!S_TMEM || j + 1 >= NB) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) { if (!S_TMEM) { sa_nxt[c] = 0.f; sb_nxt[c] = 0.f; } }
         }
         if (second) { tmem_ld4(tc + 4 * j, ca_old); tmem_ld4(tc + 4 * (NB - 1 - j), cb_old); }
         else {
@@ -124,25 +113,21 @@ __device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, 
         }
         tmem_wait_ld(pa_nxt, pb_nxt);
         tmem_wait_ld(ca_old, cb_old);
-        if (S_TMEM) tmem_wait_ld(sa_nxt, sb_nxt);
+        tmem_wait_ld(sa_nxt, sb_nxt);
         float va[4], vb[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            // chain A at node 4j-1+c: S[ka] is column 4j+c of the S array = element c of group j
+            // chain A at node 4j-1+c: its cell is column 4j+c of the slowness array = element c of group j
             const float own_a = a.pk;
-            const float sk = S_TMEM ? sa_cur[c] : sa[0];
-            float v = eikf::chain_a_node(a, (c < 3) ? pa_cur[c + 1] : pa_nxt[0], sk, tie);
+            float v = eikf::chain_a_node(a, (c < 3) ? pa_cur[c + 1] : pa_nxt[0], sa_cur[c], tie);
             v = fminf(v, ca_old[c]);
             va[c] = (MASKED && !need) ? own_a : v;
-            sa += 32;
-            // chain B at node kb = CA-2-4j-c: S[kb-1] is column kb of the S array = element 2-c of group NB-1-j (c < 3),
-            // element 3 of the next lower group (c == 3)
+            // chain B at node kb = CA-2-4j-c: cell kb-1 is column kb of the slowness array = element 2-c of group NB-1-j
+            // (c < 3), element 3 of the next lower group (c == 3)
             const float own_b = b.pk;
-            const float hs1 = S_TMEM ? ((c < 3) ? sb_cur[2 - c] : sb_nxt[3]) : sb[0];
-            float w = eikf::chain_b_node(b, (c < 3) ? pb_cur[2 - c] : pb_nxt[3], hs1);
+            float w = eikf::chain_b_node(b, (c < 3) ? pb_cur[2 - c] : pb_nxt[3], (c < 3) ? sb_cur[2 - c] : sb_nxt[3]);
             w = fminf(w, cb_old[3 - c]);
             vb[3 - c] = (MASKED && !need) ? own_b : w;
-            sb -= 32;
         }
         tmem_st4(tc + 4 * j, va);
         tmem_st4(tc + 4 * (NB - 1 - j), vb);

@@ -275,15 +275,12 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
     float* tieP = b.tie_scratch + (size_t)blockIdx.x * kPipeTieFloats + 32 + lane;   // node k at tieP[k*32], k = -1 .. CA-2
     float* tieC = tieP + (size_t)CA * 32;
     float* tieS = tieC + (size_t)CA * 32 + 32;                             // cell k at tieS[k*32], k = -2 .. CA-1
-    // slowness column of the third TMEM set of each lane quarter (unused: two sets per quarter)
-    float* S3 = nullptr;
-    const int nz = b.nz, ke = nz - 1, mx = b.nxmod - 1, nodes = b.nxmod * b.nz;
+    const int nz = b.nz, ke = nz - 1, mx = b.nxmod - 1;
     const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
     const int n_solves = n_items * nz;
     const int n_tasks = (n_solves + 31) >> 5;
     const size_t wfloats = ((size_t)D.wx * D.nz + kFineNodes) * 32;
     float* Wbase = b.scratch + (size_t)(blockIdx.x * kPipeWarps + warp) * wfloats + lane;
-    (void)nodes;
 
     for (;;) {
         int task = 0;
@@ -318,8 +315,8 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
         if (!__any_sync(0xffffffffu, live)) { pipe_release(&ctl.slice_free, sl, lane); continue; }
         // ---- move the task into a TMEM set of this warp's lane quarter, give the slice back
         const int ts = pipe_acquire(&ctl.tset_free[quarter], lane);
-        // sets 0 and 1: columns [0,192) and [192,384) = past | current | slowness; set 2: columns [384,512) = past | current
-        const bool s_tmem = ts < 2;
+        // sets 0 and 1 of the quarter: columns [0,192) and [192,384) = past | current | slowness (columns [384,512) stay unused:
+        // a third set with its slowness column in shared memory costs two slices and was slower, profiles/README.md)
         const uint32_t tset = ctl.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ts * 3 * CA);
         const uint32_t tS = tset + 2 * CA;
         for (int q = 0; q < NB; q++) {
@@ -331,13 +328,8 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
                 w[c] = (live && k >= 0 && k < ke) ? L.S[(size_t)k * 32] : kInfM;
             }
             eikm::tmem_st4(tset + 4 * q, v);
-            if (s_tmem) eikm::tmem_st4(tS + 4 * q, w);
-            else {
-#pragma unroll
-                for (int c = 0; c < 4; c++) S3[(long)(4 * q - 1 + c) * 32] = w[c];
-            }
+            eikm::tmem_st4(tS + 4 * q, w);
         }
-        if (!s_tmem) { S3[-64] = kInfM; S3[(long)(CA - 1) * 32] = kInfM; }   // (not reached: two sets per quarter)
         eikm::tmem_wait_st();
         pipe_release(&ctl.slice_free, sl, lane);
         // ---- march in tensor memory
@@ -346,11 +338,8 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
         const int xhi = __reduce_max_sync(0xffffffffu, live ? x1 : -1);
         for (int line = xlo + 1; line <= mx; line++) {
             const bool need = live && line > x1;
-            bool tie;
-            if (s_tmem) tie = (line <= xhi) ? eikm::tmem_sweep<NB, true, true>(need, tp, tc, nullptr, tS)
-                                            : eikm::tmem_sweep<NB, false, true>(need, tp, tc, nullptr, tS);
-            else tie = (line <= xhi) ? eikm::tmem_sweep<NB, true, false>(need, tp, tc, S3, 0u)
-                                     : eikm::tmem_sweep<NB, false, false>(need, tp, tc, S3, 0u);
+            const bool tie = (line <= xhi) ? eikm::tmem_sweep<NB, true>(need, tp, tc, tS)
+                                           : eikm::tmem_sweep<NB, false>(need, tp, tc, tS);
             eikm::tmem_wait_st();
             if (__any_sync(0xffffffffu, tie)) {
                 // an exact tie in the past column: the literal walk (march_sweep) on a shared-memory copy, under the CTA's lock
@@ -359,11 +348,7 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
                 for (int q = 0; q < NB; q++) {
                     float v[4], w[4];
                     eikm::tmem_ld4(tp + 4 * q, v);
-                    if (s_tmem) eikm::tmem_ld4(tS + 4 * q, w);
-                    else {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) w[c] = S3[(long)(4 * q - 1 + c) * 32];
-                    }
+                    eikm::tmem_ld4(tS + 4 * q, w);
                     eikm::tmem_wait_ld(v, w);
 #pragma unroll
                     for (int c = 0; c < 4; c++) { tieP[(long)(4 * q - 1 + c) * 32] = v[c]; tieS[(long)(4 * q - 1 + c) * 32] = w[c]; }
