@@ -271,6 +271,8 @@ def main():
     ap.add_argument("--events", type=int, default=200)
     ap.add_argument("--stations", type=int, default=50)
     ap.add_argument("--proposals", default="P", help="proposal letters of a step (P = full forward recomputation)")
+    ap.add_argument("--iters-per-step", type=int, default=1,
+                    help="Metropolis-Hastings iterations per chain in one mq_step call (>= 4: desynchronised stepping, for mixed proposal strings)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of host time for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -288,7 +290,7 @@ def main():
                 f"({2 * args.events * args.stations} picks), Example grid h=2 km 200x200x62 (eikonal plane 282x62), "
                 f"<=20 layers, proposal '{args.proposals}' (P_full: 2*nz eikonal solves + full misfit per proposal)")
     config = {"workload": workload, "chains_per_gpu": args.chains, "events": args.events, "stations": args.stations,
-              "grid": "282x62", "proposal_string": args.proposals, "parallelism": f"chains sharded x{n_gpus}, no collective",
+              "grid": "282x62", "proposal_string": args.proposals, "iterations_per_step": args.iters_per_step, "parallelism": f"chains sharded x{n_gpus}, no collective",
               "l2": "per-step working set (tables 0.9 GB + solver scratch > 1 GB per GPU) exceeds the 126 MB L2"}
 
     import mcmc_eq_b200 as mq
@@ -328,7 +330,7 @@ def main():
     smp.sync()
     smp.timer_start(0)
     for _ in range(args.steps):
-        smp.step(1, args.proposals)
+        smp.step(args.iters_per_step, args.proposals)
     ms = smp.timer_stop(0)
     smp.sync()
     ms = barrier_max(dist, ms, device)
@@ -336,7 +338,7 @@ def main():
     eik_ms, eik_n, solves_per_launch = smp.profile(False)
     clk = clocks.stop()
     counts, ll, rms = smp.stats()
-    proposals = args.chains * n_gpus * args.steps
+    proposals = args.chains * n_gpus * args.steps * args.iters_per_step
     value = proposals / (ms / 1000.0)
 
     # ---- roofline of the dominant kernel (eikonal) ----------------------------------------------------------

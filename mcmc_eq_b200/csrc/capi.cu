@@ -48,7 +48,7 @@ cudaError_t alloc_view(EvalView* v, int n)
     if ((e = dalloc(&v->r_idx, n))) return e;
     if ((e = dalloc(&v->r_d, 4 * (size_t)n))) return e;
     if ((e = dalloc(&v->ev_only, n))) return e;
-    v->pres_over = nullptr; v->sres_over = nullptr;
+    v->pres_over = nullptr; v->sres_over = nullptr; v->hold = nullptr;
     return cudaSuccess;
 }
 void free_view(EvalView* v)

@@ -116,11 +116,18 @@ struct SamplerDev {
     int32_t* r_accept;   // [n]
     double* r_newll;     // [n]
     int32_t* r_qidx;     // [n] injected event index of a Q proposal
+    // desynchronised stepping (mq_step): iterations a chain still owes to the current call, and what it does in the
+    // current pass: 0 = evaluated and decided, 1 = idle, 2 = parked with a proposal that waits for its travel-time tables
+    int32_t* todo;       // [n] or nullptr (lock-step passes)
+    int32_t* hold;       // [n] or nullptr
+    int32_t* pass_stat;  // [2] parked chains, chains that can still propose after this pass
 };
 struct Sampler : SamplerDev {
     std::string over_host;
     bool started;
+    int32_t *todo_buf, *hold_buf, *stat_buf;   // storage of todo / hold / pass_stat, handed to the kernels by dev_desync() only
     SamplerDev dev() const { return *this; }
+    SamplerDev dev_desync() const { SamplerDev d = *this; d.todo = todo_buf; d.hold = hold_buf; d.pass_stat = stat_buf; return d; }
 };
 
 struct SamplerParams {
@@ -269,6 +276,11 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
     if (c >= p.n) return;
     const mq_config& g = p.cfg;
     const int n = p.n;
+    if (s.hold) {   // desynchronised stepping: parked chains keep their pending proposal, finished ones idle
+        if (s.hold[c] == 2) { atomicAdd(&s.pass_stat[0], 1); return; }
+        if (s.todo[c] <= 0) { s.hold[c] = 1; return; }
+        s.hold[c] = 0;
+    }
     // default: nothing to evaluate
     v.q_idx[c] = -1; v.r_idx[c] = -1; v.ev_only[c] = -2;
     const int mc = hd.mcur[c], ec = hd.ecur[c];
@@ -424,19 +436,48 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
         v.ev_only[c] = -1; v.ebuf[c] = 1 - ec;
         s.rebuilt[c] = calct;
         if (p.cfg.eikonal == 1 && p.cfg.aflag != 1) {
+            const bool park = s.hold && ok;      // the tables are built later, together with those of other parked chains
             for (int ph = 0; ph < 2; ph++) {
                 if (!(calct & (1 << ph))) continue;
                 const int tb = 1 - hd.tcur[2 * c + ph];
                 v.tbuf[2 * c + ph] = tb;
+                if (park) continue;
                 const int item = atomicAdd(hd.n_items, 1);
                 hd.item_chain[item] = c; hd.item_phase[item] = ph;
                 hd.item_tab[item] = hd.tab + (((size_t)tb * n + c) * 2 + ph) * p.tab_stride;
             }
+            if (park && calct) s.hold[c] = 2;
         }
     }
     if (p.cfg.aflag == 1) v.ev_only[c] = -2;   // prior sampling: no likelihood (src/misfit.c:61)
     if (!ok) { s.not_valid[c] = 1; v.ev_only[c] = -2; }
     s.draws[c] = rng.draws;
+    if (s.hold) {
+        if (s.hold[c] == 2) atomicAdd(&s.pass_stat[0], 1);
+        else if (s.todo[c] > 1) atomicAdd(&s.pass_stat[1], 1);
+    }
+}
+
+// Desynchronised stepping, the pass that builds tables: every parked chain queues its table rebuilds and is evaluated
+// and decided in this pass, every other chain idles.
+__global__ void flush_parked_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView v)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n) return;
+    if (s.hold[c] != 2) {
+        s.hold[c] = 1;
+        if (s.todo[c] > 0) atomicAdd(&s.pass_stat[1], 1);
+        return;
+    }
+    s.hold[c] = 0;
+    const int calct = s.rebuilt[c];
+    for (int ph = 0; ph < 2; ph++) {
+        if (!(calct & (1 << ph))) continue;
+        const int item = atomicAdd(hd.n_items, 1);
+        hd.item_chain[item] = c; hd.item_phase[item] = ph;
+        hd.item_tab[item] = hd.tab + (((size_t)v.tbuf[2 * c + ph] * p.n + c) * 2 + ph) * p.tab_stride;
+    }
+    if (s.todo[c] > 1) atomicAdd(&s.pass_stat[1], 1);
 }
 
 // ---- replay: the proposal comes from a recorded stream instead of the RNG ------------------------------
@@ -493,6 +534,10 @@ __global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.n) return;
+    if (s.hold) {   // desynchronised stepping: only chains evaluated in this pass are decided; an iteration is used up
+        if (s.hold[c] != 0) return;
+        s.todo[c]--;
+    }
     const char kind = (char)s.kind[c];
     if (kind == 0) return;   // finished chain
     const mq_config& g = p.cfg;
@@ -765,6 +810,7 @@ static int sampler_get(Handle* h, Sampler** out)
     TRY(dz(&s->wz, n * h->md)); TRY(dz(&s->wvp, n * h->md)); TRY(dz(&s->wvs, n * h->md));
     TRY(alloc_snapshot(&s->out, h)); TRY(alloc_snapshot(&s->best, h));
     TRY(dz(&s->r_alpha, n)); TRY(dz(&s->r_accept, n)); TRY(dz(&s->r_newll, n)); TRY(dz(&s->r_qidx, n));
+    TRY(dz(&s->todo_buf, n)); TRY(dz(&s->hold_buf, n)); TRY(dz(&s->stat_buf, 2));
     const std::string a = balance(h->cfg.dstring_start, h->ne, h->ns, 10), b = balance(h->cfg.dstring_main, h->ne, h->ns, 20);
     s->len_start = (int)a.size(); s->len_main = (int)b.size();
     TRY(upload_string(&s->ps_start, a)); TRY(upload_string(&s->ps_main, b));
@@ -788,6 +834,7 @@ void sampler_destroy(Handle* h)
     free_snapshot(&s->out); free_snapshot(&s->best);
     cudaFree(s->ps_start); cudaFree(s->ps_main); cudaFree(s->ps_over);
     cudaFree(s->u_inject); cudaFree(s->r_alpha); cudaFree(s->r_accept); cudaFree(s->r_newll); cudaFree(s->r_qidx);
+    cudaFree(s->todo_buf); cudaFree(s->hold_buf); cudaFree(s->stat_buf);
     cudaFree(h->prop_view.pres_over); cudaFree(h->prop_view.sres_over);
     h->prop_view.pres_over = nullptr; h->prop_view.sres_over = nullptr;
     delete s;
@@ -832,6 +879,81 @@ extern "C" int mq_init_chains(mq_handle* hh)
     return start_sampler_state(h, s);
 }
 
+// ---- desynchronised stepping -----------------------------------------------------------------------------------------
+// Chains are independent, so nothing obliges them to advance in lock-step.  In a lock-step pass of a mixed proposal
+// string only the chains that drew a velocity-model proposal (5 of 24 with the Example string) rebuild tables: the
+// eikonal launch is a fifth full and the pass lasts as long as one warp-task.  Here a chain runs through its cheap
+// proposals (hypocentre, station correction, noise) pass by pass until it draws one that needs tables, then parks;
+// when most chains are parked one pass builds all their tables in a single full launch, decides them and sets them
+// going again.  Every chain draws from its own counter-based stream, so its trajectory is the lock-step one, bit for
+// bit (tests/test_sampler_gpu.py).  MCMCEQ_DESYNC=0 turns it off.
+static bool desync_wanted(const Handle* h, int n_iters)
+{
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("MCMCEQ_DESYNC");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    return enabled && n_iters >= 4 && h->cfg.eikonal == 1 && h->cfg.aflag != 1;
+}
+
+static int finish_pass(Handle* h, Sampler* s, const SamplerParams& p, const EvalView& pv, const SamplerDev& d, int32_t stat[2])
+{
+    cudaStream_t st = h->stream;
+    const int grid = (h->n + 63) / 64;
+    MQ_CUDA(launch_misfit(h, pv));
+    MQ_CUDA(launch_totals(h, pv));
+    SamplerDev free_running = d;
+    free_running.u_inject = nullptr;
+    accept_kernel<<<grid, 64, 0, st>>>(p, *h, free_running, pv);
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    snapshot_kernel<<<h->n, 128, 0, st>>>(p, *h, s->dev());
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    MQ_CUDA(cudaMemcpyAsync(stat, s->stat_buf, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MQ_CUDA(cudaStreamSynchronize(st));
+    return MQ_OK;
+}
+
+static int step_desync(Handle* h, Sampler* s, const SamplerParams& p, int n_iters, int use_override)
+{
+    cudaStream_t st = h->stream;
+    const int grid = (h->n + 63) / 64;
+    const SamplerDev d = s->dev_desync();
+    EvalView pv = h->prop_view;
+    pv.hold = s->hold_buf;
+    {
+        std::vector<int32_t> todo((size_t)h->n, n_iters);
+        MQ_CUDA(cudaMemcpyAsync(s->todo_buf, todo.data(), todo.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        MQ_CUDA(cudaMemsetAsync(s->hold_buf, 0, (size_t)h->n * sizeof(int32_t), st));
+        MQ_CUDA(cudaStreamSynchronize(st));
+    }
+    int32_t stat[2] = {0, h->n};     // parked chains, chains that can still propose
+    for (;;) {
+        const int parked = stat[0], active = stat[1];
+        if (parked == 0 && active == 0) break;
+        // build tables when four fifths of the chains that are still at work wait for them, or nobody else can move
+        const bool flush = parked > 0 && (active == 0 || 5L * parked >= 4L * (parked + active));
+        MQ_CUDA(cudaMemsetAsync(s->stat_buf, 0, 2 * sizeof(int32_t), st));
+        if (flush) {
+            MQ_CUDA(cudaMemsetAsync(h->n_items, 0, sizeof(int32_t), st));
+            flush_parked_kernel<<<grid, 64, 0, st>>>(p, *h, d, pv);
+            count_launch();
+            MQ_CUDA(cudaGetLastError());
+            MQ_CUDA(launch_rasterise(h, pv, 2 * parked));
+            MQ_CUDA(launch_tables(h, 2 * parked));
+        } else {
+            propose_kernel<<<grid, 64, 0, st>>>(p, *h, d, pv, use_override);
+            count_launch();
+            MQ_CUDA(cudaGetLastError());
+        }
+        const int rc = finish_pass(h, s, p, pv, d, stat);
+        if (rc != MQ_OK) return rc;
+    }
+    return MQ_OK;
+}
+
 extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override)
 {
     if (!hh || n_iters < 0) { set_error("mq_step: bad argument"); return MQ_ERR_ARG; }
@@ -859,6 +981,7 @@ extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override
     const SamplerParams p = make_params(h);
     cudaStream_t st = h->stream;
     const int grid = (h->n + 63) / 64;
+    if (desync_wanted(h, n_iters)) return step_desync(h, s, p, n_iters, use_override);
     for (int it = 0; it < n_iters; it++) {
         MQ_CUDA(cudaMemsetAsync(h->n_items, 0, sizeof(int32_t), st));
         propose_kernel<<<grid, 64, 0, st>>>(p, *h, s->dev(), h->prop_view, use_override);

@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(128, 8) misfit_kernel(MisfitParams p)
     const long task = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (task >= (long)p.n * p.ne) return;
     const int c = (int)(task / p.ne), e = (int)(task - (long)c * p.ne);
+    if (p.v.hold && p.v.hold[c] != 0) return;
     const int only = p.v.ev_only[c];
     if (only == -2 || (only >= 0 && only != e)) return;
 
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(128) totals_kernel(int n, int ne, EvalView v, 
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n) return;
+    if (v.hold && v.hold[c] != 0) return;
     const int only = v.ev_only[c];
     if (only == -2) {   // nothing re-evaluated (noise proposal): the sums are those of the current model
         if (lane < 8) mf_eval[8 * (size_t)c + lane] = mf_cur[8 * (size_t)c + lane];

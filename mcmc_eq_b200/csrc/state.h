@@ -45,6 +45,7 @@ struct EvalView {
     int32_t* ev_only;  // [n]   >= 0: evaluate only this event (result in evq/oq); -1: all; -2: none
     float* pres_over;  // [n][ns] proposed station corrections given in full (replay mode, mq_replay_step) or nullptr
     float* sres_over;
+    const int32_t* hold;   // [n] or nullptr: chains with hold[c] != 0 are not evaluated in this pass (desynchronised stepping, chain.cu)
 };
 
 // On-device posterior accumulation = pass 1 of the reference's analyse_eq (src/analyse_eq.c:496-643) applied to every
