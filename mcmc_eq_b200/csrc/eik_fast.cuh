@@ -54,6 +54,7 @@ struct Dims {
     int col_len;         // column buffer: indices -1 .. col_len (col_len >= max(nz, 43); -1 and nz hold sentinels)
     int row_len;         // row buffer: top row from the front, bottom row from the back, never more than
                          // nz + 3 nodes between them while both are needed; >= max(nz + 4, 48)
+    int row_march;       // rows whose past times do not decrease away from the axis are swept in lock-step (row_march)
 };
 
 EIK_HD Dims make_dims(int nx, int nz)
@@ -64,6 +65,7 @@ EIK_HD Dims make_dims(int nx, int nz)
     if (D.wx > nx) D.wx = nx;
     D.col_len = nz > 43 ? nz : 43;
     D.row_len = (nz + 4 > 48) ? nz + 4 : 48;
+    D.row_march = 1;
     return D;
 }
 // floats per lane of the three shared arrays: S[-1..nz-1], COL[-1..col_len], ROW[0..row_len-1]
@@ -262,15 +264,70 @@ EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inpl
     return slow;
 }
 
+#ifdef EIKF_STATS
+static long g_stats[12];
+#endif
+
+// ---- rows in lock-step ---------------------------------------------------------------------------------------
+// In a laterally homogeneous medium the first arrival at a given depth never comes earlier further away from the
+// source axis, so the past row of a row sweep (nodes 0 .. ke, the axis at 0) is non-decreasing -- up to rounding,
+// which is why it is checked.  The reference's walk over such a row is one segment: the local minimum it finds is
+// node 0, timed by 1-D transmission, then one pass outwards (fast_sweep<true>: SEG at k = 0, the walk towards kb ends
+// at once, the walk towards ke runs through).  All lanes are at the same node at the same time: straight-line code,
+// no per-lane state machine.  In place like fast_sweep's row discipline; a lane whose head-wave test fires stops
+// writing and reports the line for the slow path, exactly where fast_sweep would.
+// R: node k at R[k*stride]; ke per lane.  *mono: the NEW row is non-decreasing as well (known for free).
+EIK_HD bool row_is_monotone(bool act, const float* R, int stride, int ke)
+{
+    bool ok = true;
+    float prev = act ? R[0] : 0.f;
+    for (int k = 1; EIKF_ANY(act && k <= ke); k++) {
+        if (act && k <= ke) {
+            const float cur = R[(long)k * stride];
+            ok = ok && (cur - prev >= 0.f);
+            prev = cur;
+        }
+    }
+    return ok;
+}
+
+EIK_HD bool row_march(bool act, float* R, int stride, int ke, float c, float c2, float* Wt, long wstride, bool* mono)
+{
+    const bool hw = c2 < c;
+    bool slow = false, mn = true;
+    float pn = 0.f, cn = 0.f;
+    if (act) {
+        pn = R[0];
+        const float est = pn + eik::fmin_ref(kInf, c);       // 1-D transmission in front of the minimum (node 0: no cell before it)
+        cn = (est < kInf) ? est : kInf;
+        R[0] = cn;
+        if (Wt) Wt[0] = cn;
+    }
+    for (int k = 1; EIKF_ANY(act && !slow && k <= ke); k++) {
+        if (act && !slow && k <= ke) {
+            const float pk = R[(long)k * stride];
+            const float cv = node_update(kInf, pk, pn, cn, c, c, true);
+            if (hw && headwave_fires(cv, cn, c2)) slow = true;
+            R[(long)k * stride] = cv;
+            if (Wt) Wt[(long)k * wstride] = cv;
+            mn = mn && (cv - cn >= 0.f);
+            pn = pk; cn = cv;
+        }
+    }
+    *mono = mn && !slow;
+#ifdef EIKF_STATS
+    if (act) { g_stats[9]++; if (slow) g_stats[10]++; }
+#endif
+    return slow;
+}
+
 // ---- the march: one full-depth column from the previous one ------------------------------------------------
 // The same walk as fast_sweep<false> in its ping-pong discipline, specialised for the steady state of a solve
 // (kb = 0, ke = my, coarse medium, no write-through, no slow path).  P and C have indices -1 .. ke+1 whose two
 // end slots hold kStop, so a walk ends at the array ends by the very test that ends it at a local maximum of the
 // past column; S[-1] = S[ke] = INF stand for the cells the reference does not look at.
 constexpr float kStop = -1.0e30f;
-#ifdef EIKF_STATS
-static long g_stats[8];
-#endif
+
 
 EIK_HD void march_sweep(bool act, const float* P, float* C, const float* S, int ke, int* hint)
 {
@@ -516,6 +573,22 @@ EIK_HD int slow_line(float* t, const Box& b, const Medium& m, const Lane& L, int
     return g.status;
 }
 
+// May the row sweep of this round take row_march?  Every lane that sweeps (act) must have a non-decreasing past row:
+// known from the previous sweep of that row (then only the node the last column sweep appended is new), else checked.
+EIK_HD bool row_ready(bool act, const float* R, int stride, int ke, bool known)
+{
+    bool ok = true;
+    if (act) {
+        if (known) ok = (ke < 1) || (R[(long)ke * stride] - R[(long)(ke - 1) * stride] >= 0.f);
+    }
+    const bool need_check = act && !known;
+    if (EIKF_ANY(need_check)) {
+        const bool m = row_is_monotone(need_check, R, stride, ke);
+        if (need_check) ok = m;
+    }
+    return !EIKF_ANY(act && !ok);
+}
+
 // ---- expanding box + march on one grid, all lanes of the warp together --------------------------------
 // FINE selects the medium type of the slow path.  out/rows: receiver-row output of the coarse grid
 // (nullptr on the refined grid); out[r*out_rstride + x] receives t[x][rows[r]].
@@ -537,6 +610,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
     float* col = L.COL;      // the lane's current right column
     float* spare = L.ROW + LS;   // second column buffer (indices -1..ny), valid once the rows are no longer needed
     int hint = -1;           // first local minimum of the current column (known on the march)
+    bool mono_top = false, mono_bot = false;   // the top / bottom row is known not to decrease away from the axis
     if (xbox_end) *xbox_end = boxphase ? -1 : b.X1;
     // cell slowness of a row strip, with the masked dummy row of the coarse grid
     auto rowS = [&](int cy) -> float { return (!FINE && cy >= b.my) ? kInf : med.cell(cy); };
@@ -599,13 +673,24 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 }
                 const float c = need ? rowS(line) : 1.f;
                 const float c2 = (need && line - 1 >= 0) ? rowS(line - 1) : kInf;   // far < 0: no head wave
-                const bool s2 = fast_sweep<true>(need && !slow, L.ROW, L.ROW, LS, true, 0, b.X1, med, c, c2,
-                                                 T + (size_t)line * LS, (long)b.ny * LS, nullptr);
+                const bool fastlane = need && !slow;
+                bool s2;
+                if (D.row_march && row_ready(fastlane, L.ROW, LS, b.X1, mono_top))
+                    s2 = row_march(fastlane, L.ROW, LS, b.X1, c, c2, T + (size_t)line * LS, (long)b.ny * LS, &mono_top);
+                else {
+#ifdef EIKF_STATS
+                    if (fastlane) g_stats[8]++;
+#endif
+                    s2 = fast_sweep<true>(fastlane, L.ROW, L.ROW, LS, true, 0, b.X1, med, c, c2,
+                                          T + (size_t)line * LS, (long)b.ny * LS, nullptr);
+                    mono_top = false;
+                }
                 if (need && (slow || s2)) {
                     const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, -1, 0, b.X1, refill)
                                         : slow_line<1>(T, b, cm, L, RL, line, -1, 0, b.X1, refill);
                     if (rc != eik::kOk) status = rc;
                     b.preset_up = 0;
+                    mono_top = false;
                 }
                 if (need) col[(size_t)line * LS] = L.ROW[(size_t)b.X1 * LS];
             }
@@ -657,12 +742,23 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 const float c = need ? rowS(line - 1) : 1.f;
                 const float c2 = need ? rowS(line) : kInf;
                 float* bot = L.ROW + (size_t)(RL - 1) * LS;
-                const bool s2 = fast_sweep<true>(need && !slow, bot, bot, -LS, true, 0, b.X1, med, c, c2,
-                                                 T + (size_t)line * LS, (long)b.ny * LS, nullptr);
+                const bool fastlane = need && !slow;
+                bool s2;
+                if (D.row_march && row_ready(fastlane, bot, -LS, b.X1, mono_bot))
+                    s2 = row_march(fastlane, bot, -LS, b.X1, c, c2, T + (size_t)line * LS, (long)b.ny * LS, &mono_bot);
+                else {
+#ifdef EIKF_STATS
+                    if (fastlane) g_stats[8]++;
+#endif
+                    s2 = fast_sweep<true>(fastlane, bot, bot, -LS, true, 0, b.X1, med, c, c2,
+                                          T + (size_t)line * LS, (long)b.ny * LS, nullptr);
+                    mono_bot = false;
+                }
                 if (need && (slow || s2)) {
                     const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, 1, 0, b.X1, !slow)
                                         : slow_line<1>(T, b, cm, L, RL, line, 1, 0, b.X1, !slow);
                     if (rc != eik::kOk) status = rc;
+                    mono_bot = false;
                 }
                 if (need) col[(size_t)line * LS] = L.ROW[(size_t)(RL - 1 - b.X1) * LS];
             }

@@ -83,7 +83,17 @@ cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream)
 
 
 // ---- warp-synchronous kernel ---------------------------------------------------------------------------
-static eikf::Dims fast_dims(int nxmod, int nz) { return eikf::make_dims(nxmod, nz); }
+static eikf::Dims fast_dims(int nxmod, int nz)
+{
+    static int row_march = -1;
+    if (row_march < 0) {
+        const char* e = getenv("MCMCEQ_ROW_MARCH");
+        row_march = (e && e[0] == '0') ? 0 : 1;      // lock-step row sweeps (eik_fast.cuh: row_march), on unless MCMCEQ_ROW_MARCH=0
+    }
+    eikf::Dims D = eikf::make_dims(nxmod, nz);
+    D.row_march = row_march;
+    return D;
+}
 static size_t fast_smem_floats_per_warp(const eikf::Dims& D) { return (size_t)eikf::smem_floats_per_lane(D) * 32; }
 static size_t fast_scratch_floats_per_warp(const eikf::Dims& D) { return ((size_t)D.wx * D.nz + kFineNodes) * 32; }
 
@@ -225,6 +235,22 @@ constexpr int kPipeCA = 64;          // nodes -1 .. 62 per TMEM column array: nz
 constexpr int kPipeMaxCtas = 256;    // one CTA per SM; the tie scratch is sized for this many
 constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time columns + slowness column of the tie scratch
 
+// The box phase of a task, compiled as a function of its own.  Inlined into eik_pipe_kernel next to the tensor-memory
+// march, nvcc 12.9 produced a kernel whose box-region output depended on unrelated code in run_grid (receiver row 0 left
+// at INF; found when the lock-step row sweeps were added, bisected on the GPU: any variant with the call inlined and the
+// top-row site present failed, every variant with the call out of line passed).  tests/test_pipe_gpu.py compares the
+// two kernels bit for bit and guards this.
+// Arguments by value: as references they would live in the caller's stack frame and be re-read through it.
+// x1 receives the column at which the box phase ended (-1: nothing left to march).
+__device__ __noinline__ int solve_warp_call(eikf::Dims D, eikf::Lane L, eikf::LaneTask t, const int* rows, int n_rows, int* x1_out)
+{
+    int x1 = -1;
+    t.hand_x1 = &x1;
+    const int rc = eikf::solve_warp(D, L, t, rows, n_rows);
+    *x1_out = x1;
+    return rc;
+}
+
 struct PipeCtl {
     uint32_t tmem;                   // base address of the CTA's 512 TMEM columns
     unsigned slice_free;             // bit i: shared-memory slice i is free
@@ -300,7 +326,7 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
         t.iz = 0; t.slow = nullptr; t.out = nullptr; t.out_rstride = 0; t.full = nullptr;
         int x1 = -1;
         t.hand_col = L.COL;          // the last column of the box phase already sits there
-        t.hand_x1 = &x1;
+        t.hand_x1 = nullptr;         // set inside solve_warp_call
         if (t.valid) {
             t.iz = g / n_items;
             const int item = g - t.iz * n_items;
@@ -309,7 +335,7 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
             t.out = tab + (size_t)t.iz * b.xpitch;
             t.out_rstride = (long)nz * b.xpitch;
         }
-        const int rc = eikf::solve_warp(D, L, t, b.rows, b.n_rows);
+        const int rc = solve_warp_call(D, L, t, b.rows, b.n_rows, &x1);
         if (t.valid && b.status_min && rc < 0) atomicMin(b.status_min, rc);
         const bool live = x1 >= 0 && x1 < mx;
         if (!__any_sync(0xffffffffu, live)) { pipe_release(&ctl.slice_free, sl, lane); continue; }

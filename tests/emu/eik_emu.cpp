@@ -30,5 +30,5 @@ extern "C" int emu_fast_time_2d(const float* s, int nx, int ny, int iz, float* t
     return eikf::solve_warp(D, L, task, rows, n_rows);
 }
 #ifdef EIKF_STATS
-extern "C" void emu_stats(long* out) { for (int i = 0; i < 8; i++) out[i] = eikf::g_stats[i]; }
+extern "C" void emu_stats(long* out) { for (int i = 0; i < 12; i++) out[i] = eikf::g_stats[i]; }
 #endif

@@ -37,8 +37,8 @@ np.savez(sys.argv[1], **out)
 """
 
 
-def _run(path, pipe, n):
-    env = dict(os.environ, MCMCEQ_EIKONAL_PIPE="1" if pipe else "0")
+def _run(path, pipe, n, row_march=True):
+    env = dict(os.environ, MCMCEQ_EIKONAL_PIPE="1" if pipe else "0", MCMCEQ_ROW_MARCH="1" if row_march else "0")
     r = subprocess.run([sys.executable, "-c", SCRIPT % util.ROOT, path, str(n)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
     return dict(np.load(path))
@@ -51,3 +51,15 @@ def test_pipelined_kernel_is_bit_identical_to_the_fused_kernel(tmp_path):
     b = _run(str(tmp_path / "pipe.npz"), True, 1230)
     for k in a:
         assert np.array_equal(a[k], b[k]), (k, int((a[k] != b[k]).sum()), a[k].size, float(np.nanmax(np.abs(a[k].astype(float) - b[k].astype(float)))))
+
+
+def test_lock_step_row_sweeps_are_bit_identical_to_the_general_walk(tmp_path):
+    """Rows whose past times do not decrease away from the axis are swept in lock-step (eik_fast.cuh: row_march) instead of by
+    the per-lane walk (MCMCEQ_ROW_MARCH=0): the same nodes from the same neighbours, so identical bits -- in both kernels."""
+    a = _run(str(tmp_path / "walk.npz"), False, 70, row_march=False)
+    b = _run(str(tmp_path / "rows.npz"), False, 70)
+    c = _run(str(tmp_path / "pipe_walk.npz"), True, 1230, row_march=False)
+    d = _run(str(tmp_path / "pipe_rows.npz"), True, 1230)
+    for x, y in ((a, b), (c, d)):
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
