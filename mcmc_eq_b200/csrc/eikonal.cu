@@ -116,11 +116,13 @@ __global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims 
     L.WF = L.W + (size_t)D.wx * D.nz * 32;
     const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
     const int n_solves = b.src_iz ? b.n_solves : n_items * b.nz;
-    const int n_tasks = (n_solves + 31) >> 5;
+    const int lpt = b.lanes_per_task;           // lanes of a warp that carry a solve
+    const int n_tasks = (n_solves + lpt - 1) / lpt;
 
     for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        int g = task * 32 + lane;
-        if (b.order) g = b.order[g];
+        int g = task * lpt + lane;
+        if (lane >= lpt) g = -1;
+        else if (b.order) g = b.order[g];
         eikf::LaneTask t;
         t.valid = g >= 0 && g < n_solves;
         t.iz = 0; t.slow = nullptr; t.out = nullptr; t.out_rstride = 0; t.full = nullptr; t.hand_col = nullptr; t.hand_x1 = nullptr;
@@ -490,14 +492,29 @@ cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream)
         resident = eik_fast_max_warps(b.nxmod, b.nz, dev);
         configured_for = dev * 100000 + b.nz;
     }
-    const int n_tasks = (n_solves + 31) / 32;
     // scratch was sized for max_warps warps of the generic kernel, which is never less per warp
     const size_t have = (size_t)b.max_warps * eik_scratch_floats_per_warp(b.nxmod, b.nz);
     long warps = (long)(have / fast_scratch_floats_per_warp(D));
     if (warps > resident) warps = resident;
+    // A launch with fewer warp-tasks than warps that can be resident lasts as long as one task, and a task is the shorter
+    // the fewer lanes have to wait for each other in the box phase: spread it over the idle warps.
+    EikBatch bb = b;
+    static int lanes_env = -1;
+    if (lanes_env < 0) {
+        const char* e = getenv("MCMCEQ_EIKONAL_LANES");     // 32 / 16 / 8 / 4: fixed; unset: chosen per launch
+        lanes_env = e ? atoi(e) : 0;
+    }
+    if (!bb.lanes_per_task) bb.lanes_per_task = lanes_env;
+    int lpt = (bb.lanes_per_task == 32 || bb.lanes_per_task == 16 || bb.lanes_per_task == 8 || bb.lanes_per_task == 4) ? bb.lanes_per_task : 0;
+    if (!lpt) {
+        lpt = 32;
+        while (lpt > 4 && ((long)n_solves + lpt / 2 - 1) / (lpt / 2) <= warps) lpt /= 2;
+    }
+    bb.lanes_per_task = lpt;
+    const int n_tasks = (n_solves + lpt - 1) / lpt;
     if (warps > n_tasks) warps = n_tasks;
     if (warps < 1) warps = 1;
-    eik_fast_kernel<<<(unsigned)warps, 32, smem, stream>>>(b, D);
+    eik_fast_kernel<<<(unsigned)warps, 32, smem, stream>>>(bb, D);
     count_launch();
     return cudaGetLastError();
 }
