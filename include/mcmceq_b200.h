@@ -158,6 +158,10 @@ int mq_tables_restore(mq_handle* h);
  * (ttt[j][iz][i], src/misfit.c:281-288); phase 1 = P, 2 = S.  Recomputes that chain's table
  * with every receiver row kept; meant for parity tests and the setup_table_new shim. */
 int mq_get_table(mq_handle* h, int chain, int phase, float* ttt);
+/* The receiver rows of that table as they are stored on the device (what cal_fit_newx can ever read of it,
+ * src/misfit.c:91,109): rows_out[r][iz][i] = ttt[row_index[r]][iz][i], r < n_rows.  Returns n_rows (>= 0) or a negative
+ * status; either output may be NULL (call with both NULL to learn n_rows). */
+int mq_get_rows(mq_handle* h, int chain, int phase, float* rows_out, int32_t* row_index);
 
 /* Per-pick predictions of one chain after mq_forward: what cal_fit_newx prints with out=1
  * (src/misfit.c:130-143).  resid / tpred are [n_picks] in the handle's pick order. */

@@ -116,6 +116,7 @@ def lib() -> C.CDLL:
         L.mq_tables_save.argtypes = [C.c_void_p]
         L.mq_tables_restore.argtypes = [C.c_void_p]
         L.mq_get_table.argtypes = [C.c_void_p, C.c_int, C.c_int, fp]
+        L.mq_get_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, C.POINTER(C.c_int32)]
         L.mq_get_predictions.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.mq_init_chains.argtypes = [C.c_void_p]
         L.mq_step.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
@@ -298,6 +299,18 @@ class Sampler:
         t = np.zeros((self.nz, self.nz, self.nxmod), np.float32)
         check(lib().mq_get_table(self.h, chain, phase, _p(t)))
         return t
+
+    def rows(self, chain: int, phase: int):
+        """(rows[n_rows][nz][nxmod], row_index[n_rows]): the stored receiver rows of a chain's table."""
+        n = lib().mq_get_rows(self.h, chain, phase, None, None)
+        if n < 0:
+            check(n)
+        t = np.zeros((n, self.nz, self.nxmod), np.float32)
+        idx = np.zeros(n, np.int32)
+        n2 = lib().mq_get_rows(self.h, chain, phase, _p(t), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+        if n2 < 0:
+            check(n2)
+        return t, idx
 
     def predictions(self, chain: int):
         r = np.zeros(self.picks.n_picks, np.float32)

@@ -428,6 +428,29 @@ extern "C" int mq_sync(mq_handle* hh)
     return MQ_OK;
 }
 
+extern "C" int mq_get_rows(mq_handle* hh, int chain, int phase, float* rows_out, int32_t* row_index)
+{
+    if (!hh || chain < 0 || chain >= hh->h.n || (phase != 1 && phase != 2)) { set_error("mq_get_rows: bad argument"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    if (!h->forward_done) { set_error("mq_get_rows: no tables yet (mq_forward first)"); return MQ_ERR_STATE; }
+    MQ_CUDA(cudaSetDevice(h->device));
+    if (row_index) for (int r = 0; r < h->n_rows; r++) row_index[r] = h->rows_host[r];
+    if (rows_out) {
+        int32_t tb = 0;
+        MQ_CUDA(d2h(&tb, h->tcur + 2 * (size_t)chain + (phase - 1), 1, h->stream));
+        MQ_CUDA(cudaStreamSynchronize(h->stream));
+        const float* src = h->tab + (((size_t)tb * h->n + chain) * 2 + (phase - 1)) * h->tab_stride;
+        std::vector<float> tmp(h->tab_stride);
+        MQ_CUDA(d2h(tmp.data(), src, h->tab_stride, h->stream));
+        MQ_CUDA(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < h->n_rows; r++)
+            for (int k = 0; k < h->nz; k++)
+                for (int i = 0; i < h->nxmod; i++)
+                    rows_out[((size_t)r * h->nz + k) * h->nxmod + i] = tmp[((size_t)r * h->nz + k) * h->xp + i];
+    }
+    return h->n_rows;
+}
+
 extern "C" int mq_get_table(mq_handle* hh, int chain, int phase, float* ttt)
 {
     if (!hh || !ttt || chain < 0 || chain >= hh->h.n || (phase != 1 && phase != 2)) { set_error("mq_get_table: bad argument"); return MQ_ERR_ARG; }

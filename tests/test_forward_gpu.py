@@ -40,6 +40,10 @@ def test_forward_matches_reference_fixtures(name):
     tab = smp.table(0, 1)
     ref = d[f"{name}_0_tabP_rows12"]
     assert (np.abs(tab[1:3] - ref) <= util.eikonal_tol(ref)).all()
+    # the rows the device keeps (mq_get_rows) are rows of that table
+    rows, idx = smp.rows(0, 1)
+    assert len(idx) >= 2 and (np.diff(idx) > 0).all()
+    assert (np.abs(rows - tab[idx]) <= util.eikonal_tol(tab[idx])).all()
     smp.close()
 
 
