@@ -124,6 +124,17 @@ EIK_HD float sqrt_pos(float r)
 #endif
 }
 
+// 0 <= x < lim for lim > 0: non-negative floats order like their bit patterns and a negative x has its sign bit set, so one
+// unsigned compare does both (x is a difference of two times or sentinels here: never NaN, never -0.0, which x - x is not).
+EIK_HD bool in_zero_lim(float x, float lim)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(x) < __float_as_uint(lim);
+#else
+    return x >= 0.f && x < lim;
+#endif
+}
+
 // ---- one node of a walk ------------------------------------------------------------------------
 // pk: past time at the node, pn/cn: past and current time at the neighbour towards the minimum,
 // c: current value of the node so far, hs0: cell between node and neighbour, hs1: next cell away
@@ -139,7 +150,7 @@ EIK_HD float node_update(float c, float pk, float pn, float cn, float hs0, float
     c = fminf(c, (dt < lim) ? est : kInf);
     const float dt2 = cn - pn;
     est = cn + sqrt_pos(fmaf(-dt2, dt2, hs0sq));                  // plane wave through the lateral side
-    c = fminf(c, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+    c = fminf(c, in_zero_lim(dt2, lim) ? est : kInf);
     c = fminf(c, use3 ? pk + hs1 : kInf);                         // 1-D transmission towards the future
     c = fminf(c, fmaf(hs0, kSqrt2, pn));                          // corner diffraction
     return c;
@@ -396,7 +407,7 @@ EIK_HD void march_sweep(bool act, const float* P, float* C, const float* S, int 
                 float cv = fminf(cold, (dt < lim) ? est : kInf);
                 const float dt2 = cn - pn;
                 est = cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
-                cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+                cv = fminf(cv, in_zero_lim(dt2, lim) ? est : kInf);
                 cv = fminf(cv, pk2 + hs1);
                 cv = fminf(cv, fmaf(s0, kSqrt2, pn));
                 C[(long)kk * LS] = cv;
@@ -457,10 +468,10 @@ EIK_HD float chain_a_node(ChainA& a, float pnext, float sk, bool& tie)
     float cv = (dt < lim) ? est : kInf;
     const float dt2 = a.cn - a.pprev;
     est = a.cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
-    cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+    cv = fminf(cv, in_zero_lim(dt2, lim) ? est : kInf);
     cv = fminf(cv, a.pk + sk);
     cv = fminf(cv, fmaf(a.sprev, kSqrt2, a.pprev));
-    const float cmin = fminf(kInf, a.pk + eik::fmin_ref(a.sprev, sk));
+    const float cmin = fminf(kInf, a.pk + fminf(a.sprev, sk));   // == fmin_ref for the positive, non-NaN cell slownesses
     const float val = up ? cv : (root ? cmin : kInf);
     a.cn = val; a.pprev = a.pk; a.pk = pnext; a.sprev = sk;
     return val;
@@ -477,10 +488,10 @@ EIK_HD float chain_b_node(ChainB& b, float pprev, float hs1)
     float cv = (dt < lim) ? est : kInf;
     const float dt2 = b.cn - b.pnx;
     est = b.cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
-    cv = fminf(cv, (dt2 >= 0.f && dt2 < lim) ? est : kInf);
+    cv = fminf(cv, in_zero_lim(dt2, lim) ? est : kInf);
     cv = fminf(cv, b.pk + hs1);
     cv = fminf(cv, fmaf(b.s0, kSqrt2, b.pnx));
-    const float cmin = fminf(kInf, b.pk + eik::fmin_ref(hs1, b.s0));
+    const float cmin = fminf(kInf, b.pk + fminf(hs1, b.s0));
     const float val = down ? cv : (root ? cmin : kInf);
     b.cn = val; b.pnx = b.pk; b.pk = pprev; b.s0 = hs1;
     return val;
