@@ -76,6 +76,50 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // value of a sentinel node (k < 0 or k > ke): above every travel time, strictly increasing with k
 __device__ __forceinline__ float sentinel(int k, int ke) { return k < 0 ? kEdge : kEdge * (1.0f + (float)(k - ke) * (1.0f / 1024.0f)); }
 
+// One group of four nodes of each chain (see tmem_sweep).  SECOND: the other chain has been at these nodes, its values
+// are read back and merged; in the first half of a column there is nothing to merge (a real node's value never exceeds
+// INF, so the merge with INF it would be is the identity).
+struct SweepRegs {
+    float pa_cur[4], pb_cur[4], sa_cur[4], sb_cur[4];
+};
+
+template <int NB, bool MASKED, bool SECOND>
+__device__ __forceinline__ void tmem_group(int j, bool need, uint32_t tp, uint32_t tc, uint32_t tS, eikf::ChainA& a, eikf::ChainB& b,
+                                           SweepRegs& r, bool& tie)
+{
+    float pa_nxt[4], pb_nxt[4], ca_old[4], cb_old[4], sa_nxt[4], sb_nxt[4];
+    if (j + 1 < NB) {
+        tmem_ld4(tp + 4 * (j + 1), pa_nxt); tmem_ld4(tp + 4 * (NB - 2 - j), pb_nxt);
+        tmem_ld4(tS + 4 * (j + 1), sa_nxt); tmem_ld4(tS + 4 * (NB - 2 - j), sb_nxt);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) { pa_nxt[c] = 4.0f * kEdge; pb_nxt[c] = 2.0f * kEdge; sa_nxt[c] = kInf; sb_nxt[c] = kInf; }
+    }
+    if (SECOND) { tmem_ld4(tc + 4 * j, ca_old); tmem_ld4(tc + 4 * (NB - 1 - j), cb_old); }
+    tmem_wait_ld(pa_nxt, pb_nxt);
+    if (SECOND) tmem_wait_ld(ca_old, cb_old);
+    tmem_wait_ld(sa_nxt, sb_nxt);
+    float va[4], vb[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        // chain A at node 4j-1+c: its cell is column 4j+c of the slowness array = element c of group j
+        const float own_a = a.pk;
+        float v = eikf::chain_a_node(a, (c < 3) ? r.pa_cur[c + 1] : pa_nxt[0], r.sa_cur[c], tie);
+        if (SECOND) v = fminf(v, ca_old[c]);
+        va[c] = (MASKED && !need) ? own_a : v;
+        // chain B at node kb = CA-2-4j-c: cell kb-1 is column kb of the slowness array = element 2-c of group NB-1-j
+        // (c < 3), element 3 of the next lower group (c == 3)
+        const float own_b = b.pk;
+        float w = eikf::chain_b_node(b, (c < 3) ? r.pb_cur[2 - c] : pb_nxt[3], (c < 3) ? r.sb_cur[2 - c] : sb_nxt[3]);
+        if (SECOND) w = fminf(w, cb_old[3 - c]);
+        vb[3 - c] = (MASKED && !need) ? own_b : w;
+    }
+    tmem_st4(tc + 4 * j, va);
+    tmem_st4(tc + 4 * (NB - 1 - j), vb);
+#pragma unroll
+    for (int c = 0; c < 4; c++) { r.pa_cur[c] = pa_nxt[c]; r.pb_cur[c] = pb_nxt[c]; r.sa_cur[c] = sa_nxt[c]; r.sb_cur[c] = sb_nxt[c]; }
+}
+
 // One column: past column in TMEM array tp, new column into array tc, slowness cells in array tS (cell k at column k+1,
 // cells -1 and ke.. = INF); all three are column addresses of this warp's lane quarter.
 // MASKED: lanes with need == false keep their past column (their box phase ended at a later column than the others').
@@ -83,57 +127,21 @@ template <int NB, bool MASKED>
 __device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, uint32_t tS)
 {
     bool tie = false;
-    float pa_cur[4], pb_cur[4], sa_cur[4], sb_cur[4];
-    tmem_ld4(tp, pa_cur);
-    tmem_ld4(tp + 4 * (NB - 1), pb_cur);
-    tmem_ld4(tS, sa_cur);
-    tmem_ld4(tS + 4 * (NB - 1), sb_cur);
-    tmem_wait_ld(pa_cur, pb_cur);
-    tmem_wait_ld(sa_cur, sb_cur);
+    SweepRegs r;
+    tmem_ld4(tp, r.pa_cur);
+    tmem_ld4(tp + 4 * (NB - 1), r.pb_cur);
+    tmem_ld4(tS, r.sa_cur);
+    tmem_ld4(tS + 4 * (NB - 1), r.sb_cur);
+    tmem_wait_ld(r.pa_cur, r.pb_cur);
+    tmem_wait_ld(r.sa_cur, r.sb_cur);
     // chain A starts at node -1 (parent -2: nothing there), chain B at node CA-2 (parent CA-1: nothing there)
-    eikf::ChainA a{2.0f * kEdge, pa_cur[0], kInf, kInf};
-    eikf::ChainB b{4.0f * kEdge, pb_cur[3], kInf, kInf};
-
+    eikf::ChainA a{2.0f * kEdge, r.pa_cur[0], kInf, kInf};
+    eikf::ChainB b{4.0f * kEdge, r.pb_cur[3], kInf, kInf};
 #pragma unroll 1
-    for (int j = 0; j < NB; j++) {
-        const bool second = j >= NB / 2;         // the other chain has been at these nodes
-        float pa_nxt[4], pb_nxt[4], ca_old[4], cb_old[4], sa_nxt[4], sb_nxt[4];
-        if (j == NB / 2) tmem_wait_st();         // its stores must have landed before they are read back
-        if (j + 1 < NB) {
-            tmem_ld4(tp + 4 * (j + 1), pa_nxt); tmem_ld4(tp + 4 * (NB - 2 - j), pb_nxt);
-            tmem_ld4(tS + 4 * (j + 1), sa_nxt); tmem_ld4(tS + 4 * (NB - 2 - j), sb_nxt);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; c++) { pa_nxt[c] = 4.0f * kEdge; pb_nxt[c] = 2.0f * kEdge; sa_nxt[c] = kInf; sb_nxt[c] = kInf; }
-        }
-        if (second) { tmem_ld4(tc + 4 * j, ca_old); tmem_ld4(tc + 4 * (NB - 1 - j), cb_old); }
-        else {
-#pragma unroll
-            for (int c = 0; c < 4; c++) { ca_old[c] = kInf; cb_old[c] = kInf; }
-        }
-        tmem_wait_ld(pa_nxt, pb_nxt);
-        tmem_wait_ld(ca_old, cb_old);
-        tmem_wait_ld(sa_nxt, sb_nxt);
-        float va[4], vb[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            // chain A at node 4j-1+c: its cell is column 4j+c of the slowness array = element c of group j
-            const float own_a = a.pk;
-            float v = eikf::chain_a_node(a, (c < 3) ? pa_cur[c + 1] : pa_nxt[0], sa_cur[c], tie);
-            v = fminf(v, ca_old[c]);
-            va[c] = (MASKED && !need) ? own_a : v;
-            // chain B at node kb = CA-2-4j-c: cell kb-1 is column kb of the slowness array = element 2-c of group NB-1-j
-            // (c < 3), element 3 of the next lower group (c == 3)
-            const float own_b = b.pk;
-            float w = eikf::chain_b_node(b, (c < 3) ? pb_cur[2 - c] : pb_nxt[3], (c < 3) ? sb_cur[2 - c] : sb_nxt[3]);
-            w = fminf(w, cb_old[3 - c]);
-            vb[3 - c] = (MASKED && !need) ? own_b : w;
-        }
-        tmem_st4(tc + 4 * j, va);
-        tmem_st4(tc + 4 * (NB - 1 - j), vb);
-#pragma unroll
-        for (int c = 0; c < 4; c++) { pa_cur[c] = pa_nxt[c]; pb_cur[c] = pb_nxt[c]; sa_cur[c] = sa_nxt[c]; sb_cur[c] = sb_nxt[c]; }
-    }
+    for (int j = 0; j < NB / 2; j++) tmem_group<NB, MASKED, false>(j, need, tp, tc, tS, a, b, r, tie);
+    tmem_wait_st();                      // the other chain's stores must have landed before they are read back
+#pragma unroll 1
+    for (int j = NB / 2; j < NB; j++) tmem_group<NB, MASKED, true>(j, need, tp, tc, tS, a, b, r, tie);
     return need && tie;
 }
 
