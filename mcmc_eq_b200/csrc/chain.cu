@@ -887,13 +887,24 @@ extern "C" int mq_init_chains(mq_handle* hh)
 // when most chains are parked one pass builds all their tables in a single full launch, decides them and sets them
 // going again.  Every chain draws from its own counter-based stream, so its trajectory is the lock-step one, bit for
 // bit (tests/test_sampler_gpu.py).  MCMCEQ_DESYNC=0 turns it off.
-static bool desync_wanted(const Handle* h, int n_iters)
+// true when every letter of the string is a proposal that rebuilds tables: nothing to run ahead with
+static bool only_table_proposals(const char* str)
+{
+    if (!str || !*str) return false;
+    for (const char* q = str; *q; q++)
+        if (!strchr("PVMBD", *q)) return false;
+    return true;
+}
+
+static bool desync_wanted(const Handle* h, int n_iters, const char* override_str)
 {
     static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("MCMCEQ_DESYNC");
         enabled = (e && e[0] == '0') ? 0 : 1;
     }
+    if (override_str && *override_str) { if (only_table_proposals(override_str)) return false; }
+    else if (only_table_proposals(h->cfg.dstring_start) && only_table_proposals(h->cfg.dstring_main)) return false;
     return enabled && n_iters >= 4 && h->cfg.eikonal == 1 && h->cfg.aflag != 1;
 }
 
@@ -981,7 +992,7 @@ extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override
     const SamplerParams p = make_params(h);
     cudaStream_t st = h->stream;
     const int grid = (h->n + 63) / 64;
-    if (desync_wanted(h, n_iters)) return step_desync(h, s, p, n_iters, use_override);
+    if (desync_wanted(h, n_iters, use_override ? proposal_override : nullptr)) return step_desync(h, s, p, n_iters, use_override);
     for (int it = 0; it < n_iters; it++) {
         MQ_CUDA(cudaMemsetAsync(h->n_items, 0, sizeof(int32_t), st));
         propose_kernel<<<grid, 64, 0, st>>>(p, *h, s->dev(), h->prop_view, use_override);
