@@ -439,6 +439,11 @@ cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t s
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     int n_slices = (int)(((size_t)smem_max - tie - 256) / slice);
     if (n_slices > 12) n_slices = 12;
+    {
+        static int env_slices = -1;      // experiment: fewer slices than fit (profiles/README.md)
+        if (env_slices < 0) { const char* e = getenv("MCMCEQ_PIPE_SLICES"); env_slices = e ? atoi(e) : 0; }
+        if (env_slices >= 2 && env_slices < n_slices) n_slices = env_slices;
+    }
     if (n_slices < 2) return cudaErrorInvalidValue;
     const size_t smem = (size_t)n_slices * slice + tie;
     static size_t configured = 0;     // largest dynamic shared-memory size the kernel has been opted in for
