@@ -225,14 +225,14 @@ cudaError_t eik_order_tasks(const EikBatch& b, int32_t* order, void* work, size_
 
 // ---- the pipelined kernel: box phase in shared memory, march in tensor memory, in ONE persistent CTA per SM --------------
 // The fused kernel holds 9 warps per SM because every warp keeps 24.7 KB of shared memory for its whole life, although it
-// only needs it for the box phase (per-lane indices); the march (warp-uniform indices) can live in TMEM.  Here 16 warps
+// only needs it for the box phase (per-lane indices); the march (warp-uniform indices) can live in TMEM.  Here 12 warps
 // per SM share kSlices shared-memory slices and 8 TMEM sets (past column, current column, slowness column = 3 x 64
 // columns; two sets per lane quarter): a warp takes a slice for the box phase of a task, moves the task's last column and
 // slowness column into a TMEM set, gives the slice back and marches in tensor memory.  At any time about half of the warps
-// are in the latency-bound box phase and half in the issue-bound march, and there are 16 of them instead of 9.
+// are in the latency-bound box phase and half in the issue-bound march, and there are 12 of them instead of 9 (with 154 registers each instead of 128: no spills).
 // Resources are taken in a fixed order (slice, then TMEM set; the tie scratch last and never while waiting for anything
 // else), holders of a TMEM set never wait for a slice: no cycle, no deadlock.
-constexpr int kPipeWarps = 16;
+constexpr int kPipeWarps = 12;     // measured 10 .. 20: 12 - 13 are best at 1024 chains, 12 - 16 equal at 8192 (profiles/README.md)
 constexpr int kPipeCA = 64;          // nodes -1 .. 62 per TMEM column array: nz <= 62
 constexpr int kPipeMaxCtas = 256;    // one CTA per SM; the tie scratch is sized for this many
 constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time columns + slowness column of the tie scratch

@@ -46,7 +46,7 @@ def _run(path, pipe, n, row_march=True):
 
 def test_pipelined_kernel_is_bit_identical_to_the_fused_kernel(tmp_path):
     """One persistent CTA per SM, 16 warps sharing a pool of shared-memory slices (box phase) and a pool of TMEM sets (march)."""
-    # the pipelined kernel only takes launches with work for all 148 x 16 warps: 1230 chains x 2 phases x 61 depths
+    # the pipelined kernel only takes launches with work for all 148 x 12 warps: 1230 chains x 2 phases x 61 depths
     a = _run(str(tmp_path / "fused.npz"), False, 1230)
     b = _run(str(tmp_path / "pipe.npz"), True, 1230)
     for k in a:
