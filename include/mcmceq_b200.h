@@ -29,6 +29,9 @@ extern "C" {
                                     the reference prints and exit(0)s, src/misfit.c:93,111         */
 #define MQ_ERR_NOMEM (-6)
 #define MQ_ERR_STATE (-7)        /* call made in the wrong order                                  */
+#define MQ_ERR_RETRY (-8)        /* a start value could not be drawn inside its bounds (the reference's
+                                    rand_gauss_bounded would loop for ever, src/mcmc_eq.c:149-159)  */
+#define MQ_ERR_BUSY (-9)         /* both drain batches are in flight (mq_drain_begin)             */
 
 #define MQ_MAX_CLASSES 8         /* 4 pick classes x {P,S}: index = 2*class + (phase == S)        */
 
@@ -221,12 +224,32 @@ typedef struct mq_record {
 /* Called once per record; pointers are valid during the call only.  Return non-zero to stop. */
 typedef int (*mq_record_fn)(void* user, const mq_record* rec);
 
-/* Hands every pending decimated record to fn, then clears them.  Each chain holds at most one
- * pending record, so call this at least every `deci` iterations; *n_lost (may be NULL) counts
- * records that were overwritten before being drained. */
+/* Decimated records wait in a device-side ring of `slots` records per chain (default 4, 1..64; MCMCEQ_RING_SLOTS
+ * overrides the default).  A chain whose ring is full drops the new record and counts it as lost; a ring of R slots
+ * therefore survives R * deci iterations between two drains.  Call before mq_init_chains / the first mq_step. */
+int mq_set_ring(mq_handle* h, int slots);
+
+/* Synchronous drain: hands every pending decimated record to fn (the records of a chain in the order they were
+ * produced) and frees their ring slots.  *n_lost (may be NULL) = records dropped since the previous drain. */
 int mq_drain(mq_handle* h, mq_record_fn fn, void* user, int* n_lost);
-/* which = 0: current state of `chain`, 1: its best-RMS model so far. */
+
+/* Asynchronous drain, the output path for thousands of chains (the reference writes 1 + noq + nos lines per record,
+ * src/mcmc_eq.c:234-248, from the sampling loop itself, :1163).  mq_drain_begin enqueues -- on a second stream, behind
+ * the steps issued so far -- a kernel that packs the pending records into a staging buffer and frees their ring slots;
+ * it returns at once and later mq_step calls run next to it.  The batch then belongs to the caller and may be used from
+ * ANY host thread (a writer thread), while the handle goes on stepping: mq_batch_wait blocks until the records are in
+ * pinned host memory (one cudaMemcpyAsync of exactly the packed records), mq_batch_deliver calls fn once per record,
+ * mq_batch_release gives the batch back.  A handle owns two batches; MQ_ERR_BUSY when both are in flight. */
+typedef struct mq_batch mq_batch;
+int mq_drain_begin(mq_handle* h, mq_batch** batch);
+int mq_batch_wait(mq_batch* batch, int* n_records, int* n_lost);
+int mq_batch_deliver(mq_batch* batch, mq_record_fn fn, void* user);
+int mq_batch_release(mq_batch* batch);
+
+/* which = 0: current state of `chain`, 1: its best-RMS model so far.  mq_snapshot_all: the same for every chain of the
+ * handle with bulk copies (fn is called n_chains times, chain 0 first). */
 int mq_snapshot(mq_handle* h, int chain, int which, mq_record_fn fn, void* user);
+int mq_snapshot_all(mq_handle* h, int which, mq_record_fn fn, void* user);
 
 int mq_sync(mq_handle* h);
 
@@ -277,6 +300,14 @@ int mq_temper_swap(mq_handle* h, int64_t round, int32_t* n_swapped);
  * launch performs when every chain rebuilds both tables. */
 int mq_profile(mq_handle* h, int enable, double* eikonal_ms, int64_t* eikonal_launches,
                int64_t* solves_per_full_launch);
+
+/* Which eikonal kernel the launches counted by the last mq_profile call took: launches[k] / ms[k], k = 0 generic
+ * (time field in global memory), 1 fused (one warp per CTA, shared memory), 2 pipelined (shared-memory box phase +
+ * tensor-memory march), 3 fine-grid (planes that do not fit a shared-memory slice); both arrays hold MQ_EIK_KERNELS
+ * entries.  mq_eikonal_kernel_name(k) is the kernel's symbol name as ncu prints it. */
+#define MQ_EIK_KERNELS 4
+int mq_profile_kernels(mq_handle* h, int64_t* launches, double* ms);
+const char* mq_eikonal_kernel_name(int k);
 
 /* CUDA-event stopwatch on the handle's stream: stop = 0 records the start of `slot` (0..15), stop = 1 records
  * the end, waits for it and returns the device time between the two in *elapsed_ms. */

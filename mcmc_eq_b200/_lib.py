@@ -123,7 +123,16 @@ def lib() -> C.CDLL:
         L.mq_replay_step.argtypes = [C.c_void_p, C.POINTER(MqReplay)]
         L.mq_get_stats.argtypes = [C.c_void_p, lp, dp, dp]
         L.mq_drain.argtypes = [C.c_void_p, RECORD_FN, C.c_void_p, C.POINTER(C.c_int)]
+        L.mq_set_ring.argtypes = [C.c_void_p, C.c_int]
+        L.mq_drain_begin.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.mq_batch_wait.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.mq_batch_deliver.argtypes = [C.c_void_p, RECORD_FN, C.c_void_p]
+        L.mq_batch_release.argtypes = [C.c_void_p]
         L.mq_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_int, RECORD_FN, C.c_void_p]
+        L.mq_snapshot_all.argtypes = [C.c_void_p, C.c_int, RECORD_FN, C.c_void_p]
+        L.mq_profile_kernels.argtypes = [C.c_void_p, lp, dp]
+        L.mq_eikonal_kernel_name.argtypes = [C.c_int]
+        L.mq_eikonal_kernel_name.restype = C.c_char_p
         L.mq_sync.argtypes = [C.c_void_p]
         L.mq_timer.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
         L.mq_profile.argtypes = [C.c_void_p, C.c_int, dp, lp, lp]
@@ -427,5 +436,33 @@ class Sampler:
         recs = self._collect(lambda fn: check(lib().mq_drain(self.h, fn, None, C.byref(lost))))
         return recs, lost.value
 
+    def set_ring(self, slots: int):
+        check(lib().mq_set_ring(self.h, slots))
+
+    def drain_begin(self):
+        """Start an asynchronous drain; returns the batch (finish it with drain_finish, possibly on another thread)."""
+        b = C.c_void_p()
+        check(lib().mq_drain_begin(self.h, C.byref(b)))
+        return b
+
+    def drain_finish(self, batch):
+        """-> (records, n_lost) of a batch begun with drain_begin; releases the batch."""
+        n, lost = C.c_int(0), C.c_int(0)
+        check(lib().mq_batch_wait(batch, C.byref(n), C.byref(lost)))
+        recs = self._collect(lambda fn: check(lib().mq_batch_deliver(batch, fn, None)))
+        check(lib().mq_batch_release(batch))
+        assert len(recs) == n.value
+        return recs, lost.value
+
     def snapshot(self, chain: int, which: int = 0):
         return self._collect(lambda fn: check(lib().mq_snapshot(self.h, chain, which, fn, None)))[0]
+
+    def snapshot_all(self, which: int = 0):
+        return self._collect(lambda fn: check(lib().mq_snapshot_all(self.h, which, fn, None)))
+
+    def profile_kernels(self):
+        """{kernel name: (launches, ms)} of the eikonal launches counted by the last profile() call."""
+        n = np.zeros(4, np.int64)
+        ms = np.zeros(4, np.float64)
+        check(lib().mq_profile_kernels(self.h, _p(n, lp), _p(ms, dp)))
+        return {lib().mq_eikonal_kernel_name(k).decode(): (int(n[k]), float(ms[k])) for k in range(4) if n[k] > 0}

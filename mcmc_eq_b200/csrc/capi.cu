@@ -108,6 +108,11 @@ extern "C" int mq_destroy(mq_handle* hh)
     cudaFree(h->evq); cudaFree(h->oq); cudaFree(h->mf_eval); cudaFree(h->resid); cudaFree(h->tpred);
     cudaFree(h->item_chain); cudaFree(h->item_phase); cudaFree(h->n_items); cudaFree(h->slow); cudaFree(h->item_tab);
     cudaFree(h->solve_status); cudaFree(h->scratch); cudaFree(h->eik_order); cudaFree(h->eik_order_work); cudaFree(h->eik_task_counter); cudaFree(h->eik_tie_scratch);
+    if (h->host_flags) cudaFreeHost(h->host_flags);
+    if (h->flags_ev) cudaEventDestroy(h->flags_ev);
+    for (int i = 0; i < 2; i++)
+        for (int k = 0; k < 16; k++)
+            if (h->timer_ev[i][k]) cudaEventDestroy(h->timer_ev[i][k]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete hh;
     return MQ_OK;
@@ -212,9 +217,12 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
     TRY(dalloc(&h->evsum, 2 * n * ne * 8)); TRY(dalloc(&h->origin, 2 * n * ne));
     TRY(dalloc(&h->mf, n * 8)); TRY(dalloc(&h->ll, n)); TRY(dalloc(&h->rms, n)); TRY(dalloc(&h->misfit, n));
     TRY(dalloc(&h->err, 1));
+    TRY(cudaHostAlloc((void**)&h->host_flags, 2 * sizeof(int32_t), cudaHostAllocDefault));
+    h->host_flags[0] = h->host_flags[1] = 0;
+    TRY(cudaEventCreateWithFlags(&h->flags_ev, cudaEventDisableTiming));
     TRY(alloc_view(&h->cur_view, n_chains)); TRY(alloc_view(&h->prop_view, n_chains));
     TRY(dalloc(&h->evq, n * 8)); TRY(dalloc(&h->oq, n)); TRY(dalloc(&h->mf_eval, n * 8));
-    TRY(dalloc(&h->resid, n * np));
+    // h->resid ([n][np] per-pick scratch) is allocated by launch_misfit when it is first needed
     TRY(dalloc(&h->item_chain, 2 * n)); TRY(dalloc(&h->item_phase, 2 * n)); TRY(dalloc(&h->n_items, 1));
     TRY(dalloc(&h->slow, 2 * n * h->nz)); TRY(dalloc(&h->item_tab, 2 * n)); TRY(dalloc(&h->solve_status, 1));
     {
@@ -317,24 +325,53 @@ extern "C" int mq_get_models(mq_handle* hh, mq_models* m)
     return MQ_OK;
 }
 
-static int check_device_errors(Handle* h)
+// ---- device error words -------------------------------------------------------------------------------------
+// Kernels raise errors by setting bits of h->err (kErrStatcor, kErrRetry) or a negative h->solve_status.  Calls that
+// return results to the host read them synchronously (check_device_errors); mq_step in lock-step mode stays asynchronous:
+// it leaves a copy of the two words in pinned memory (flags_enqueue) and the next call that synchronises -- mq_sync,
+// mq_get_stats, mq_drain, ... -- or the next mq_step that finds the copy complete reports them (flags_poll).
+namespace mq {
+static int decode_flags(Handle* h, int32_t err, int32_t status)
+{
+    if (err != 0) {
+        cudaMemsetAsync(h->err, 0, sizeof(int32_t), h->stream);
+        if (err & kErrStatcor) { set_error("ERROR points to invalid station correction (src/misfit.c:93,111)"); return MQ_ERR_STATCOR; }
+        set_error("a start value could not be drawn inside its bounds after 100000 tries (config lines 9-16, 36-40)");
+        return MQ_ERR_RETRY;
+    }
+    if (status != 0) {
+        cudaMemsetAsync(h->solve_status, 0, sizeof(int32_t), h->stream);
+        set_error("eikonal solver status %d", status);
+        return MQ_ERR_SOLVER;
+    }
+    return MQ_OK;
+}
+int check_device_errors(Handle* h)
 {
     int32_t flags[2] = {0, 0};
     MQ_CUDA(d2h(&flags[0], h->err, 1, h->stream));
     MQ_CUDA(d2h(&flags[1], h->solve_status, 1, h->stream));
     MQ_CUDA(cudaStreamSynchronize(h->stream));
-    if (flags[0] != 0) {
-        cudaMemsetAsync(h->err, 0, sizeof(int32_t), h->stream);
-        set_error("ERROR points to invalid station correction (src/misfit.c:93,111)");
-        return MQ_ERR_STATCOR;
-    }
-    if (flags[1] != 0) {
-        cudaMemsetAsync(h->solve_status, 0, sizeof(int32_t), h->stream);
-        set_error("eikonal solver status %d", flags[1]);
-        return MQ_ERR_SOLVER;
-    }
+    h->flags_pending = false;
+    return decode_flags(h, flags[0], flags[1]);
+}
+int flags_enqueue(Handle* h)
+{
+    MQ_CUDA(d2h(&h->host_flags[0], h->err, 1, h->stream));
+    MQ_CUDA(d2h(&h->host_flags[1], h->solve_status, 1, h->stream));
+    MQ_CUDA(cudaEventRecord(h->flags_ev, h->stream));
+    h->flags_pending = true;
     return MQ_OK;
 }
+int flags_poll(Handle* h, bool wait)
+{
+    if (!h->flags_pending) return MQ_OK;
+    if (wait) MQ_CUDA(cudaEventSynchronize(h->flags_ev));
+    else if (cudaEventQuery(h->flags_ev) != cudaSuccess) { cudaGetLastError(); return MQ_OK; }
+    h->flags_pending = false;
+    return decode_flags(h, h->host_flags[0], h->host_flags[1]);
+}
+}  // namespace mq
 
 // forward of the CURRENT state, device side only (no host copies)
 namespace mq {
@@ -425,7 +462,7 @@ extern "C" int mq_sync(mq_handle* hh)
     if (!hh) return MQ_ERR_ARG;
     MQ_CUDA(cudaSetDevice(hh->h.device));
     MQ_CUDA(cudaStreamSynchronize(hh->h.stream));
-    return MQ_OK;
+    return flags_poll(&hh->h, true);
 }
 
 extern "C" int mq_get_rows(mq_handle* hh, int chain, int phase, float* rows_out, int32_t* row_index)
@@ -527,21 +564,30 @@ extern "C" int mq_profile(mq_handle* hh, int enable, double* eikonal_ms, int64_t
     return MQ_OK;
 }
 
+extern "C" int mq_profile_kernels(mq_handle* hh, int64_t* launches, double* ms)
+{
+    if (!hh) { set_error("mq_profile_kernels: null"); return MQ_ERR_ARG; }
+    double m[kEikKernels]; long n[kEikKernels];
+    profile_by_kernel(&hh->h, m, n);
+    for (int k = 0; k < kEikKernels; k++) { if (launches) launches[k] = n[k]; if (ms) ms[k] = m[k]; }
+    return MQ_OK;
+}
+extern "C" const char* mq_eikonal_kernel_name(int k) { return eik_kernel_name(k); }
+
 // ---- device timers on the handle's stream (bench.py times K steps with these) ---------------------
-static cudaEvent_t g_timer_ev[2][16];
 extern "C" int mq_timer(mq_handle* hh, int slot, int stop, double* elapsed_ms)
 {
     if (!hh || slot < 0 || slot >= 16) { set_error("mq_timer: bad argument"); return MQ_ERR_ARG; }
     Handle* h = &hh->h;
     MQ_CUDA(cudaSetDevice(h->device));
-    cudaEvent_t& e = g_timer_ev[stop ? 1 : 0][slot];
+    cudaEvent_t& e = h->timer_ev[stop ? 1 : 0][slot];
     if (!e) MQ_CUDA(cudaEventCreate(&e));
     MQ_CUDA(cudaEventRecord(e, h->stream));
     if (stop) {
         MQ_CUDA(cudaEventSynchronize(e));
         float ms = 0.f;
-        if (!g_timer_ev[0][slot]) { set_error("mq_timer: stop without start"); return MQ_ERR_STATE; }
-        MQ_CUDA(cudaEventElapsedTime(&ms, g_timer_ev[0][slot], e));
+        if (!h->timer_ev[0][slot]) { set_error("mq_timer: stop without start"); return MQ_ERR_STATE; }
+        MQ_CUDA(cudaEventElapsedTime(&ms, h->timer_ev[0][slot], e));
         if (elapsed_ms) *elapsed_ms = ms;
     }
     return MQ_OK;

@@ -93,10 +93,28 @@ struct Philox {
     }
 };
 
-struct Snapshot {   // a full copy of a chain's state, for the decimated output and the best model
+struct Snapshot {   // a full copy of a chain's state (the best model so far), SoA over chains
     int32_t* dim; float *z, *vp, *vpvs, *eq, *origin, *pres, *sres, *noise;
     double* rms; int64_t* number; int32_t* code; int32_t* flag;
 };
+
+// Decimated records (print_model_raw, src/mcmc_eq.c:234-248, written at :1163): a device-side ring of `slots` packed
+// records per chain.  accept_kernel decides that the model just accepted is a record (pend), snapshot_kernel writes the
+// chain's state into slot wr % slots and publishes it (wr + 1); a drain (pack_records_kernel, on the copy stream)
+// copies the records [rd, wr) of every chain into a staging buffer and frees them (rd = wr).  A full ring drops the NEW
+// record and counts it (lost): published slots are never overwritten, so a drain may run next to later steps.
+// Record = kRecHead words of header (chain, code, dim, -, number as int64, rms as double), noise[8], z[md], vp[md],
+// vpvs[md], eq[3 ne], origin[ne], pres[ns], sres[ns], padded to a multiple of four floats.
+constexpr int kRecHead = 8;
+struct Ring {
+    float* data;          // [n][slots][rec_floats]
+    int32_t *wr, *rd;     // [n] records published / handed to a drain so far
+    int32_t* lost;        // [n] records dropped since the last drain
+    int32_t* pend;        // [n] 0: nothing, 1: store the state as a record, 2: ring full (posterior accumulation only)
+    int64_t* number; int32_t* code; double* rms;   // [n] header of the pending record
+    int slots, rec_floats;
+};
+__host__ __device__ inline int rec_floats_of(int md, int ne, int ns) { return (kRecHead + 8 + 3 * md + 4 * ne + 2 * ns + 3) / 4 * 4; }
 
 struct SamplerDev {
     int64_t *acce, *reject, *counts;
@@ -107,7 +125,8 @@ struct SamplerDev {
     float* noise_new;
     double* best_rms;
     float *wz, *wvp, *wvs;   // model_valid work arrays [n][md]
-    Snapshot out, best;
+    Ring ring;
+    Snapshot best;
     char *ps_start, *ps_main, *ps_over;
     int len_start, len_main, len_over;
     // replay mode (mq_replay_step): injected uniform deviates and per-chain results of the last decision
@@ -122,9 +141,25 @@ struct SamplerDev {
     int32_t* hold;       // [n] or nullptr
     int32_t* pass_stat;  // [2] parked chains, chains that can still propose after this pass
 };
+}  // namespace mq
+// One drain in flight (include/mcmceq_b200.h: mq_batch): device staging + pinned host copy of the packed records.
+struct mq_batch {
+    mq::Handle* h;
+    int state;              // 0 free, 1 begun (pack kernel + count copy enqueued), 2 records on the host
+    float* d_stage; int cap_records, rec_floats;
+    int32_t *d_count, *h_count;     // [2] records, lost (device / pinned)
+    float* h_stage; size_t h_cap_floats;   // pinned, grown on demand
+    cudaEvent_t ev_count, ev_data;
+    int n_records, n_lost;
+};
+namespace mq {
 struct Sampler : SamplerDev {
     std::string over_host;
     bool started;
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_main;          // orders a drain behind the steps enqueued so far
+    mq_batch batch[2];
+    Snapshot cur;                 // scratch of mq_snapshot(which = 0)
     int32_t *todo_buf, *hold_buf, *stat_buf;   // storage of todo / hold / pass_stat, handed to the kernels by dev_desync() only
     SamplerDev dev() const { return *this; }
     SamplerDev dev_desync() const { SamplerDev d = *this; d.todo = todo_buf; d.hold = hold_buf; d.pass_stat = stat_buf; return d; }
@@ -266,7 +301,7 @@ __global__ void init_chains_kernel(SamplerParams p, Handle hd, SamplerDev s)
     s.draws[c] = rng.draws;
     s.acce[c] = 0; s.reject[c] = 0;
     for (int k = 0; k < 20; k++) s.counts[20 * (size_t)c + k] = 0;
-    if (!ok) atomicExch(hd.err, MQ_ERR_ARG);
+    if (!ok) atomicOr(hd.err, kErrRetry);   // a start value could not be drawn inside its bounds (the reference would loop for ever)
 }
 
 // ---- proposal (src/mcmc_eq.c:856-1130) --------------------------------------------------------
@@ -435,14 +470,16 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
         v.mbuf[c] = mo;
         v.ev_only[c] = -1; v.ebuf[c] = 1 - ec;
         s.rebuilt[c] = calct;
-        if (p.cfg.eikonal == 1 && p.cfg.aflag != 1) {
-            const bool park = s.hold && ok;      // the tables are built later, together with those of other parked chains
+        // a proposal whose retry loop gave up (!ok) is rejected without being evaluated: it queues no table rebuild
+        if (p.cfg.eikonal == 1 && p.cfg.aflag != 1 && ok) {
+            const bool park = s.hold != nullptr;      // the tables are built later, together with those of other parked chains
             for (int ph = 0; ph < 2; ph++) {
                 if (!(calct & (1 << ph))) continue;
                 const int tb = 1 - hd.tcur[2 * c + ph];
                 v.tbuf[2 * c + ph] = tb;
                 if (park) continue;
                 const int item = atomicAdd(hd.n_items, 1);
+                if (item >= 2 * n) continue;         // cannot happen (two items per chain at most); never write past the lists
                 hd.item_chain[item] = c; hd.item_phase[item] = ph;
                 hd.item_tab[item] = hd.tab + (((size_t)tb * n + c) * 2 + ph) * p.tab_stride;
             }
@@ -622,9 +659,10 @@ __global__ void accept_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalView
         // decimated output (src/mcmc_eq.c:1163) and best model (src/mcmc_eq.c:1186-1191)
         const int64_t acce = number + 1;
         if (g.deci > 0 && (acce / g.deci) * g.deci == acce) {
-            if (s.out.flag[c]) s.out.flag[c] = 3;   // previous record not drained yet: it is overwritten
-            else s.out.flag[c] = 2;                 // 2/3 = snapshot requested
-            s.out.number[c] = number; s.out.code[c] = kind; s.out.rms[c] = new_rms;
+            const int pending = s.ring.wr[c] - *(volatile int32_t*)&s.ring.rd[c];
+            if (pending >= s.ring.slots) { s.ring.pend[c] = 2; s.ring.lost[c]++; }   // ring full: the record is dropped and counted
+            else s.ring.pend[c] = 1;
+            s.ring.number[c] = number; s.ring.code[c] = kind; s.ring.rms[c] = new_rms;
         }
         if (new_rms < s.best_rms[c]) { s.best_rms[c] = new_rms; s.best.flag[c] = 2; s.best.number[c] = number; s.best.rms[c] = new_rms; }
     } else {
@@ -648,6 +686,61 @@ __device__ void snapshot_copy(const SamplerParams& p, const Handle& hd, const Sn
     for (int i = threadIdx.x; i < p.ns; i += blockDim.x) { d.pres[(size_t)c * p.ns + i] = hd.pres[(size_t)c * p.ns + i]; d.sres[(size_t)c * p.ns + i] = hd.sres[(size_t)c * p.ns + i]; }
     if (threadIdx.x < 8) d.noise[8 * (size_t)c + threadIdx.x] = hd.noise[8 * (size_t)c + threadIdx.x];
     if (threadIdx.x == 0) d.dim[c] = dim;
+}
+
+// The chain's current state as one packed record (layout: struct Ring).
+__device__ void record_write(const SamplerParams& p, const Handle& hd, const Ring& R, int c, float* rec)
+{
+    const int n = p.n, mc = hd.mcur[c], ec = hd.ecur[c];
+    const int dim = hd.dim[mc * n + c];
+    const size_t mo = ((size_t)mc * n + c) * p.md;
+    if (threadIdx.x == 0) {
+        int32_t* hi = (int32_t*)rec;
+        hi[0] = c; hi[1] = R.code[c]; hi[2] = dim; hi[3] = 0;
+        *(int64_t*)(rec + 4) = R.number[c];
+        *(double*)(rec + 6) = R.rms[c];
+    }
+    float* o = rec + kRecHead;
+    if (threadIdx.x < 8) o[threadIdx.x] = hd.noise[8 * (size_t)c + threadIdx.x];
+    o += 8;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) { o[i] = hd.z[mo + i]; o[p.md + i] = hd.vp[mo + i]; o[2 * p.md + i] = hd.vpvs[mo + i]; }
+    o += 3 * p.md;
+    for (int i = threadIdx.x; i < 3 * p.ne; i += blockDim.x) o[i] = hd.eq[(size_t)c * p.ne * 3 + i];
+    o += 3 * p.ne;
+    for (int i = threadIdx.x; i < p.ne; i += blockDim.x) o[i] = hd.origin[((size_t)ec * n + c) * p.ne + i];
+    o += p.ne;
+    for (int i = threadIdx.x; i < p.ns; i += blockDim.x) { o[i] = hd.pres[(size_t)c * p.ns + i]; o[p.ns + i] = hd.sres[(size_t)c * p.ns + i]; }
+}
+
+// Drain, device side (copy stream): the published records [rd, wr) of every chain move to the staging buffer, one
+// chain's records next to each other in order; count[0] = records packed, count[1] = records dropped since the last drain.
+__global__ void __launch_bounds__(128) pack_records_kernel(int n, Ring R, float* stage, int cap_records, int32_t* count)
+{
+    const int c = blockIdx.x;
+    __shared__ int base;
+    const int w = *(volatile int32_t*)&R.wr[c], r = R.rd[c];
+    int k = w - r;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        const int l = atomicExch(&R.lost[c], 0);
+        if (l) atomicAdd(&count[1], l);
+        base = 0;
+        if (k > 0) {
+            base = atomicAdd(&count[0], k);
+            if (base + k > cap_records) { atomicSub(&count[0], k); base = -1; }   // staging full: the records stay in the ring
+        }
+    }
+    __syncthreads();
+    if (k <= 0 || base < 0) return;
+    const int nv = R.rec_floats / 4;
+    for (int j = 0; j < k; j++) {
+        const float4* src = (const float4*)(R.data + ((size_t)c * R.slots + (r + j) % R.slots) * R.rec_floats);
+        float4* dst = (float4*)(stage + (size_t)(base + j) * R.rec_floats);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile int32_t*)&R.rd[c] = w;
 }
 
 // analyse_eq pass 1 for one decimated model (src/analyse_eq.c:564-640): per depth node the velocity of the nearest
@@ -716,11 +809,18 @@ __device__ void posterior_accumulate(const SamplerParams& p, const Handle& hd, i
 __global__ void snapshot_kernel(SamplerParams p, Handle hd, SamplerDev s)
 {
     const int c = blockIdx.x;
-    if (s.out.flag[c] >= 2) {
-        if (hd.post.on && (long long)s.out.number[c] > hd.post.burn_in) posterior_accumulate(p, hd, c);
-        snapshot_copy(p, hd, s.out, c);
+    const int pend = s.ring.pend[c];
+    if (pend) {
+        if (hd.post.on && (long long)s.ring.number[c] > hd.post.burn_in) posterior_accumulate(p, hd, c);
+        if (pend == 1) {
+            const int wr = s.ring.wr[c];
+            record_write(p, hd, s.ring, c, s.ring.data + ((size_t)c * s.ring.slots + wr % s.ring.slots) * s.ring.rec_floats);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) *(volatile int32_t*)&s.ring.wr[c] = wr + 1;   // published: a drain may take it
+        }
         __syncthreads();
-        if (threadIdx.x == 0) s.out.flag[c] = 1;   // 1 = ready for mq_drain
+        if (threadIdx.x == 0) s.ring.pend[c] = 0;
     }
     if (s.best.flag[c] >= 2) {
         snapshot_copy(p, hd, s.best, c);
@@ -735,7 +835,7 @@ __global__ void init_best_kernel(int n, const double* rms, SamplerDev s)
     if (c >= n) return;
     s.best_rms[c] = rms[c];
     s.best.flag[c] = 2; s.best.number[c] = 0; s.best.rms[c] = rms[c];
-    s.out.flag[c] = 0;
+    s.ring.wr[c] = 0; s.ring.rd[c] = 0; s.ring.lost[c] = 0; s.ring.pend[c] = 0;
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -808,7 +908,21 @@ static int sampler_get(Handle* h, Sampler** out)
     TRY(dz(&s->inv_control, n)); TRY(dz(&s->kind, n)); TRY(dz(&s->not_valid, n)); TRY(dz(&s->rebuilt, n));
     TRY(dz(&s->log_fac, n)); TRY(dz(&s->noise_new, n * 8)); TRY(dz(&s->best_rms, n));
     TRY(dz(&s->wz, n * h->md)); TRY(dz(&s->wvp, n * h->md)); TRY(dz(&s->wvs, n * h->md));
-    TRY(alloc_snapshot(&s->out, h)); TRY(alloc_snapshot(&s->best, h));
+    TRY(alloc_snapshot(&s->best, h));
+    {
+        const char* e = getenv("MCMCEQ_RING_SLOTS");
+        int slots = h->ring_slots > 0 ? h->ring_slots : (e ? atoi(e) : 4);
+        if (slots < 1) slots = 1;
+        if (slots > 64) slots = 64;
+        s->ring.slots = slots;
+        s->ring.rec_floats = rec_floats_of(h->md, h->ne, h->ns);
+        TRY(dz(&s->ring.data, n * slots * s->ring.rec_floats));
+        TRY(dz(&s->ring.wr, n)); TRY(dz(&s->ring.rd, n)); TRY(dz(&s->ring.lost, n)); TRY(dz(&s->ring.pend, n));
+        TRY(dz(&s->ring.number, n)); TRY(dz(&s->ring.code, n)); TRY(dz(&s->ring.rms, n));
+        TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        TRY(cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming));
+        memset(s->batch, 0, sizeof s->batch);
+    }
     TRY(dz(&s->r_alpha, n)); TRY(dz(&s->r_accept, n)); TRY(dz(&s->r_newll, n)); TRY(dz(&s->r_qidx, n));
     TRY(dz(&s->todo_buf, n)); TRY(dz(&s->hold_buf, n)); TRY(dz(&s->stat_buf, 2));
     const std::string a = balance(h->cfg.dstring_start, h->ne, h->ns, 10), b = balance(h->cfg.dstring_main, h->ne, h->ns, 20);
@@ -831,7 +945,21 @@ void sampler_destroy(Handle* h)
     cudaFree(s->acce); cudaFree(s->reject); cudaFree(s->counts); cudaFree(s->draws); cudaFree(s->inv_control);
     cudaFree(s->kind); cudaFree(s->not_valid); cudaFree(s->rebuilt); cudaFree(s->log_fac); cudaFree(s->noise_new);
     cudaFree(s->best_rms); cudaFree(s->wz); cudaFree(s->wvp); cudaFree(s->wvs);
-    free_snapshot(&s->out); free_snapshot(&s->best);
+    free_snapshot(&s->best);
+    if (s->cur.dim) free_snapshot(&s->cur);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    cudaFree(s->ring.data); cudaFree(s->ring.wr); cudaFree(s->ring.rd); cudaFree(s->ring.lost); cudaFree(s->ring.pend);
+    cudaFree(s->ring.number); cudaFree(s->ring.code); cudaFree(s->ring.rms);
+    for (int i = 0; i < 2; i++) {
+        mq_batch& b = s->batch[i];
+        cudaFree(b.d_stage); cudaFree(b.d_count);
+        if (b.h_count) cudaFreeHost(b.h_count);
+        if (b.h_stage) cudaFreeHost(b.h_stage);
+        if (b.ev_count) cudaEventDestroy(b.ev_count);
+        if (b.ev_data) cudaEventDestroy(b.ev_data);
+    }
+    if (s->ev_main) cudaEventDestroy(s->ev_main);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     cudaFree(s->ps_start); cudaFree(s->ps_main); cudaFree(s->ps_over);
     cudaFree(s->u_inject); cudaFree(s->r_alpha); cudaFree(s->r_accept); cudaFree(s->r_newll); cudaFree(s->r_qidx);
     cudaFree(s->todo_buf); cudaFree(s->hold_buf); cudaFree(s->stat_buf);
@@ -857,9 +985,8 @@ static int start_sampler_state(Handle* h, Sampler* s)
     snapshot_kernel<<<h->n, 128, 0, h->stream>>>(p, *h, s->dev());
     count_launch();
     MQ_CUDA(cudaGetLastError());
-    MQ_CUDA(cudaStreamSynchronize(h->stream));
     s->started = true;
-    return MQ_OK;
+    return check_device_errors(h);   // synchronises: solver status, invalid station correction, start values out of bounds
 }
 
 extern "C" int mq_init_chains(mq_handle* hh)
@@ -962,7 +1089,7 @@ static int step_desync(Handle* h, Sampler* s, const SamplerParams& p, int n_iter
         const int rc = finish_pass(h, s, p, pv, d, stat);
         if (rc != MQ_OK) return rc;
     }
-    return MQ_OK;
+    return check_device_errors(h);
 }
 
 extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override)
@@ -973,6 +1100,8 @@ extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override
     MQ_CUDA(cudaSetDevice(h->device));
     Sampler* s;
     int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    rc = flags_poll(h, false);     // an error raised by the kernels of an earlier, asynchronous call
     if (rc != MQ_OK) return rc;
     if (!s->started || !h->forward_done) {   // chains supplied through mq_set_models
         rc = start_sampler_state(h, s);
@@ -1015,7 +1144,7 @@ extern "C" int mq_step(mq_handle* hh, int n_iters, const char* proposal_override
         count_launch();
         MQ_CUDA(cudaGetLastError());
     }
-    return MQ_OK;
+    return n_iters > 0 ? flags_enqueue(h) : MQ_OK;   // stays asynchronous: reported by the next synchronising call
 }
 
 // Replay of a recorded proposal stream: see include/mcmceq_b200.h.
@@ -1097,8 +1226,7 @@ extern "C" int mq_replay_step(mq_handle* hh, const mq_replay* r)
     if (r->alpha) MQ_CUDA(cudaMemcpyAsync(r->alpha, s->r_alpha, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (r->new_ll) MQ_CUDA(cudaMemcpyAsync(r->new_ll, s->r_newll, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (r->mf) MQ_CUDA(cudaMemcpyAsync(r->mf, h->mf_eval, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    MQ_CUDA(cudaStreamSynchronize(st));
-    return MQ_OK;
+    return check_device_errors(h);
 }
 
 extern "C" int mq_get_stats(mq_handle* hh, int64_t* counts, double* loglik, double* rms)
@@ -1114,104 +1242,214 @@ extern "C" int mq_get_stats(mq_handle* hh, int64_t* counts, double* loglik, doub
     if (loglik) MQ_CUDA(cudaMemcpyAsync(loglik, h->ll, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (rms) MQ_CUDA(cudaMemcpyAsync(rms, h->rms, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MQ_CUDA(cudaStreamSynchronize(h->stream));
-    return MQ_OK;
+    return flags_poll(h, true);
 }
 
 // ---- records ---------------------------------------------------------------------------------
-static int fetch_snapshot(Handle* h, const Snapshot& d, int c, std::vector<float>& buf, mq_record* r)
+// Asynchronous path: mq_drain_begin enqueues, on the copy stream and behind everything the handle's stream holds so far,
+// the pack kernel and the copy of its two counters; it returns at once, later steps run next to it.  mq_batch_wait (any
+// host thread) waits for the counters, copies exactly the packed records into pinned memory and waits for them;
+// mq_batch_deliver hands them to the callback.  Two batches exist per handle, so one can be written to disk while the
+// next is being filled.
+static void record_view(const float* rec, int md, int ne, int ns, mq_record* r)
 {
-    const size_t md = h->md, ne = h->ne, ns = h->ns;
-    buf.resize(3 * md + 4 * ne + 2 * ns + 8);
-    float* z = buf.data(); float* vp = z + md; float* vpvs = vp + md; float* eq = vpvs + md; float* origin = eq + 3 * ne;
-    float* pres = origin + ne; float* sres = pres + ns; float* noise = sres + ns;
-    int32_t dim = 0, code = 0;
-    cudaStream_t st = h->stream;
-#define D2H(dst, src, cnt) MQ_CUDA(cudaMemcpyAsync(dst, src, (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st))
-    D2H(&dim, d.dim + c, 1); D2H(&code, d.code + c, 1); D2H(&r->number, d.number + c, 1); D2H(&r->rms, d.rms + c, 1);
-    D2H(z, d.z + c * md, md); D2H(vp, d.vp + c * md, md); D2H(vpvs, d.vpvs + c * md, md);
-    D2H(eq, d.eq + c * ne * 3, 3 * ne); D2H(origin, d.origin + c * ne, ne);
-    D2H(pres, d.pres + c * ns, ns); D2H(sres, d.sres + c * ns, ns); D2H(noise, d.noise + 8 * (size_t)c, 8);
-#undef D2H
-    MQ_CUDA(cudaStreamSynchronize(st));
-    r->chain = c; r->dim = dim; r->code = (char)code;
-    r->z = z; r->vp = vp; r->vpvs = vpvs; r->eq = eq; r->origin = origin; r->pres = pres; r->sres = sres; r->noise = noise;
+    const int32_t* hi = (const int32_t*)rec;
+    memset(r, 0, sizeof *r);
+    r->chain = hi[0]; r->code = (char)hi[1]; r->dim = hi[2];
+    memcpy(&r->number, rec + 4, sizeof(int64_t));
+    memcpy(&r->rms, rec + 6, sizeof(double));
+    const float* o = rec + kRecHead;
+    r->noise = o; o += 8;
+    r->z = o; r->vp = o + md; r->vpvs = o + 2 * md; o += 3 * (size_t)md;
+    r->eq = o; o += 3 * (size_t)ne;
+    r->origin = o; o += ne;
+    r->pres = o; r->sres = o + ns;
+    r->kind = MQ_REC_MODEL;
+}
+
+extern "C" int mq_set_ring(mq_handle* hh, int slots)
+{
+    if (!hh || slots < 1 || slots > 64) { set_error("mq_set_ring: 1 <= slots <= 64"); return MQ_ERR_ARG; }
+    if (hh->h.sampler) { set_error("mq_set_ring: call before mq_init_chains / mq_step"); return MQ_ERR_STATE; }
+    hh->h.ring_slots = slots;
+    return MQ_OK;
+}
+
+extern "C" int mq_drain_begin(mq_handle* hh, mq_batch** out)
+{
+    if (!hh || !out) { set_error("mq_drain_begin: null"); return MQ_ERR_ARG; }
+    Handle* h = &hh->h;
+    MQ_CUDA(cudaSetDevice(h->device));
+    Sampler* s;
+    int rc = sampler_get(h, &s);
+    if (rc != MQ_OK) return rc;
+    mq_batch* b = nullptr;
+    for (int i = 0; i < 2 && !b; i++)
+        if (s->batch[i].state == 0) b = &s->batch[i];
+    if (!b) { set_error("mq_drain_begin: both batches are in flight (mq_batch_release one first)"); return MQ_ERR_BUSY; }
+    if (!b->d_stage) {
+        b->h = h;
+        b->rec_floats = s->ring.rec_floats;
+        b->cap_records = h->n * s->ring.slots;
+        MQ_CUDA(cudaMalloc(&b->d_stage, (size_t)b->cap_records * b->rec_floats * sizeof(float)));
+        MQ_CUDA(cudaMalloc(&b->d_count, 2 * sizeof(int32_t)));
+        MQ_CUDA(cudaHostAlloc((void**)&b->h_count, 2 * sizeof(int32_t), cudaHostAllocDefault));
+        MQ_CUDA(cudaEventCreateWithFlags(&b->ev_count, cudaEventDisableTiming));
+        MQ_CUDA(cudaEventCreateWithFlags(&b->ev_data, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = s->copy_stream;
+    MQ_CUDA(cudaEventRecord(s->ev_main, h->stream));
+    MQ_CUDA(cudaStreamWaitEvent(cs, s->ev_main, 0));
+    MQ_CUDA(cudaMemsetAsync(b->d_count, 0, 2 * sizeof(int32_t), cs));
+    pack_records_kernel<<<h->n, 128, 0, cs>>>(h->n, s->ring, b->d_stage, b->cap_records, b->d_count);
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    MQ_CUDA(cudaMemcpyAsync(b->h_count, b->d_count, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    MQ_CUDA(cudaEventRecord(b->ev_count, cs));
+    b->state = 1; b->n_records = 0; b->n_lost = 0;
+    *out = b;
+    return MQ_OK;
+}
+
+extern "C" int mq_batch_wait(mq_batch* b, int* n_records, int* n_lost)
+{
+    if (!b || b->state == 0) { set_error("mq_batch_wait: no drain begun on this batch"); return MQ_ERR_STATE; }
+    if (b->state == 1) {
+        Handle* h = b->h;
+        Sampler* s = (Sampler*)h->sampler;
+        MQ_CUDA(cudaSetDevice(h->device));
+        MQ_CUDA(cudaEventSynchronize(b->ev_count));
+        b->n_records = b->h_count[0]; b->n_lost = b->h_count[1];
+        if (b->n_records > 0) {
+            const size_t need = (size_t)b->n_records * b->rec_floats;
+            if (need > b->h_cap_floats) {
+                if (b->h_stage) cudaFreeHost(b->h_stage);
+                b->h_stage = nullptr; b->h_cap_floats = 0;
+                const size_t cap = std::max(need + need / 2, (size_t)1 << 18);
+                MQ_CUDA(cudaHostAlloc((void**)&b->h_stage, cap * sizeof(float), cudaHostAllocDefault));
+                b->h_cap_floats = cap;
+            }
+            MQ_CUDA(cudaMemcpyAsync(b->h_stage, b->d_stage, need * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
+            MQ_CUDA(cudaEventRecord(b->ev_data, s->copy_stream));
+            MQ_CUDA(cudaEventSynchronize(b->ev_data));
+        }
+        b->state = 2;
+    }
+    if (n_records) *n_records = b->n_records;
+    if (n_lost) *n_lost = b->n_lost;
+    return MQ_OK;
+}
+
+extern "C" int mq_batch_deliver(mq_batch* b, mq_record_fn fn, void* user)
+{
+    if (!b || !fn) { set_error("mq_batch_deliver: null"); return MQ_ERR_ARG; }
+    if (b->state != 2) { const int rc = mq_batch_wait(b, nullptr, nullptr); if (rc != MQ_OK) return rc; }
+    const Handle* h = b->h;
+    for (int i = 0; i < b->n_records; i++) {
+        mq_record r;
+        record_view(b->h_stage + (size_t)i * b->rec_floats, h->md, h->ne, h->ns, &r);
+        if (fn(user, &r)) break;
+    }
+    return MQ_OK;
+}
+
+extern "C" int mq_batch_release(mq_batch* b)
+{
+    if (!b) return MQ_ERR_ARG;
+    if (b->state == 1) { const int rc = mq_batch_wait(b, nullptr, nullptr); if (rc != MQ_OK) return rc; }
+    b->state = 0;
     return MQ_OK;
 }
 
 extern "C" int mq_drain(mq_handle* hh, mq_record_fn fn, void* user, int* n_lost)
 {
     if (!hh || !fn) { set_error("mq_drain: null"); return MQ_ERR_ARG; }
+    mq_batch* b = nullptr;
+    int rc = mq_drain_begin(hh, &b);
+    if (rc != MQ_OK) return rc;
+    int lost = 0;
+    rc = mq_batch_wait(b, nullptr, &lost);
+    if (rc == MQ_OK) rc = mq_batch_deliver(b, fn, user);
+    mq_batch_release(b);
+    if (n_lost) *n_lost = lost;
+    if (rc != MQ_OK) return rc;
+    return flags_poll(&hh->h, false);
+}
+
+// Copies of whole SoA arrays, then one callback per chain: 13 transfers whatever the number of chains.
+static int deliver_soa(Handle* h, int first, int count, int kind, char code, const int32_t* d_dim, const int32_t* d_code,
+                       const int64_t* d_number, const double* d_rms, const float* d_z, const float* d_vp, const float* d_vpvs,
+                       const float* d_eq, const float* d_origin, const float* d_pres, const float* d_sres, const float* d_noise,
+                       mq_record_fn fn, void* user)
+{
+    const size_t md = h->md, ne = h->ne, ns = h->ns, k = (size_t)count, c0 = (size_t)first;
+    std::vector<int32_t> dim(k), cd(k);
+    std::vector<int64_t> number(k);
+    std::vector<double> rms(k);
+    std::vector<float> z(k * md), vp(k * md), vpvs(k * md), eq(k * ne * 3), origin(k * ne), pres(k * ns), sres(k * ns), noise(k * 8);
+    cudaStream_t st = h->stream;
+#define D2H(dst, src, off, cnt) MQ_CUDA(cudaMemcpyAsync((dst).data(), (src) + (off), (cnt) * sizeof((dst)[0]), cudaMemcpyDeviceToHost, st))
+    D2H(dim, d_dim, c0, k); D2H(cd, d_code, c0, k); D2H(number, d_number, c0, k); D2H(rms, d_rms, c0, k);
+    D2H(z, d_z, c0 * md, k * md); D2H(vp, d_vp, c0 * md, k * md); D2H(vpvs, d_vpvs, c0 * md, k * md);
+    D2H(eq, d_eq, c0 * ne * 3, k * ne * 3); D2H(origin, d_origin, c0 * ne, k * ne);
+    D2H(pres, d_pres, c0 * ns, k * ns); D2H(sres, d_sres, c0 * ns, k * ns); D2H(noise, d_noise, c0 * 8, k * 8);
+#undef D2H
+    MQ_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < k; i++) {
+        mq_record r;
+        memset(&r, 0, sizeof r);
+        r.chain = (int)(c0 + i); r.kind = kind; r.code = code ? code : (char)cd[i]; r.number = number[i]; r.dim = dim[i]; r.rms = rms[i];
+        r.z = &z[i * md]; r.vp = &vp[i * md]; r.vpvs = &vpvs[i * md]; r.eq = &eq[i * ne * 3]; r.origin = &origin[i * ne];
+        r.pres = &pres[i * ns]; r.sres = &sres[i * ns]; r.noise = &noise[i * 8];
+        if (fn(user, &r)) break;
+    }
+    return MQ_OK;
+}
+
+// gathers the current state of every chain (current model / origin buffers) into the layout of a Snapshot
+__global__ void gather_current_kernel(SamplerParams p, Handle hd, SamplerDev s, Snapshot d)
+{
+    const int c = blockIdx.x;
+    snapshot_copy(p, hd, d, c);
+    if (threadIdx.x == 0) {
+        const int64_t acce = s.acce[c];
+        d.number[c] = acce > 0 ? acce - 1 : 0;
+        d.rms[c] = hd.rms[c];
+        d.code[c] = 'S';
+    }
+}
+
+static int snapshot_range(mq_handle* hh, int first, int count, int which, mq_record_fn fn, void* user)
+{
     Handle* h = &hh->h;
     MQ_CUDA(cudaSetDevice(h->device));
     Sampler* s;
     int rc = sampler_get(h, &s);
     if (rc != MQ_OK) return rc;
-    std::vector<int32_t> flag(h->n);
-    MQ_CUDA(cudaMemcpyAsync(flag.data(), s->out.flag, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    MQ_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<float> buf;
-    int lost = 0;
-    for (int c = 0; c < h->n; c++) {
-        if (!flag[c]) continue;
-        mq_record r;
-        memset(&r, 0, sizeof r);
-        rc = fetch_snapshot(h, s->out, c, buf, &r);
-        if (rc != MQ_OK) return rc;
-        r.kind = MQ_REC_MODEL;
-        if (flag[c] == 3) lost++;
-        const int stop = fn(user, &r);
-        if (stop) break;
+    if (which == 1) {
+        const Snapshot& d = s->best;
+        return deliver_soa(h, first, count, MQ_REC_BEST, 'F', d.dim, d.code, d.number, d.rms, d.z, d.vp, d.vpvs, d.eq, d.origin,
+                           d.pres, d.sres, d.noise, fn, user);
     }
-    MQ_CUDA(cudaMemsetAsync(s->out.flag, 0, h->n * sizeof(int32_t), h->stream));
-    MQ_CUDA(cudaStreamSynchronize(h->stream));
-    if (n_lost) *n_lost = lost;
-    return MQ_OK;
+    // current state: gathered on the device into a scratch snapshot, then the same bulk copies
+    if (!s->cur.dim) MQ_CUDA(alloc_snapshot(&s->cur, h));
+    const SamplerParams p = make_params(h);
+    gather_current_kernel<<<h->n, 128, 0, h->stream>>>(p, *h, s->dev(), s->cur);
+    count_launch();
+    MQ_CUDA(cudaGetLastError());
+    const Snapshot& d = s->cur;
+    return deliver_soa(h, first, count, MQ_REC_CURRENT, 'S', d.dim, d.code, d.number, d.rms, d.z, d.vp, d.vpvs, d.eq, d.origin,
+                       d.pres, d.sres, d.noise, fn, user);
 }
 
 extern "C" int mq_snapshot(mq_handle* hh, int chain, int which, mq_record_fn fn, void* user)
 {
     if (!hh || !fn || chain < 0 || chain >= hh->h.n || which < 0 || which > 1) { set_error("mq_snapshot: bad argument"); return MQ_ERR_ARG; }
-    Handle* h = &hh->h;
-    MQ_CUDA(cudaSetDevice(h->device));
-    Sampler* s;
-    int rc = sampler_get(h, &s);
-    if (rc != MQ_OK) return rc;
-    std::vector<float> buf;
-    mq_record r;
-    memset(&r, 0, sizeof r);
-    if (which == 1) {
-        rc = fetch_snapshot(h, s->best, chain, buf, &r);
-        if (rc != MQ_OK) return rc;
-        r.kind = MQ_REC_BEST;
-        r.code = 'F';
-    } else {
-        // current state of one chain, read straight from its current buffers
-        const size_t md = h->md, ne = h->ne, ns = h->ns, n = h->n, c = (size_t)chain;
-        cudaStream_t st = h->stream;
-        int32_t mcur = 0, ecur = 0, dim = 0;
-        double rms = 0;
-        int64_t acce = 0;
-        MQ_CUDA(cudaMemcpyAsync(&mcur, h->mcur + c, sizeof mcur, cudaMemcpyDeviceToHost, st));
-        MQ_CUDA(cudaMemcpyAsync(&ecur, h->ecur + c, sizeof ecur, cudaMemcpyDeviceToHost, st));
-        MQ_CUDA(cudaMemcpyAsync(&rms, h->rms + c, sizeof rms, cudaMemcpyDeviceToHost, st));
-        MQ_CUDA(cudaMemcpyAsync(&acce, s->acce + c, sizeof acce, cudaMemcpyDeviceToHost, st));
-        MQ_CUDA(cudaStreamSynchronize(st));
-        buf.resize(3 * md + 4 * ne + 2 * ns + 8);
-        float* z = buf.data(); float* vp = z + md; float* vpvs = vp + md; float* eq = vpvs + md; float* origin = eq + 3 * ne;
-        float* pres = origin + ne; float* sres = pres + ns; float* noise = sres + ns;
-        const size_t mo = ((size_t)mcur * n + c) * md;
-#define D2H(dst, src, cnt) MQ_CUDA(cudaMemcpyAsync(dst, src, (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st))
-        D2H(&dim, h->dim + (size_t)mcur * n + c, 1);
-        D2H(z, h->z + mo, md); D2H(vp, h->vp + mo, md); D2H(vpvs, h->vpvs + mo, md);
-        D2H(eq, h->eq + c * ne * 3, 3 * ne); D2H(origin, h->origin + ((size_t)ecur * n + c) * ne, ne);
-        D2H(pres, h->pres + c * ns, ns); D2H(sres, h->sres + c * ns, ns); D2H(noise, h->noise + 8 * c, 8);
-#undef D2H
-        MQ_CUDA(cudaStreamSynchronize(st));
-        r.chain = chain; r.kind = MQ_REC_CURRENT; r.code = 'S'; r.number = acce > 0 ? acce - 1 : 0; r.dim = dim; r.rms = rms;
-        r.z = z; r.vp = vp; r.vpvs = vpvs; r.eq = eq; r.origin = origin; r.pres = pres; r.sres = sres; r.noise = noise;
-        fn(user, &r);
-        return MQ_OK;
-    }
-    fn(user, &r);
-    return MQ_OK;
+    return snapshot_range(hh, chain, 1, which, fn, user);
+}
+
+extern "C" int mq_snapshot_all(mq_handle* hh, int which, mq_record_fn fn, void* user)
+{
+    if (!hh || !fn || which < 0 || which > 1) { set_error("mq_snapshot_all: bad argument"); return MQ_ERR_ARG; }
+    return snapshot_range(hh, 0, hh->h.n, which, fn, user);
 }

@@ -39,5 +39,9 @@ __host__ __device__ inline float chain_alpha(double log_fac, double new_ll, doub
 void sampler_destroy(Handle* h);
 void comm_destroy(Handle* h);
 int forward_current_device(Handle* h, int calct);
+// device error words (capi.cu): synchronous check / copy left for a later call / report of a completed copy
+int check_device_errors(Handle* h);
+int flags_enqueue(Handle* h);
+int flags_poll(Handle* h, bool wait);
 
 }  // namespace mq

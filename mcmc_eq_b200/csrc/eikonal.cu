@@ -446,11 +446,11 @@ cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t s
     }
     if (n_slices < 2) return cudaErrorInvalidValue;
     const size_t smem = (size_t)n_slices * slice + tie;
-    static size_t configured = 0;     // largest dynamic shared-memory size the kernel has been opted in for
-    if (smem > configured) {
+    static size_t configured[64] = {0};     // per device: largest dynamic shared-memory size the kernel has been opted in for
+    if (dev < 0 || dev >= 64 || smem > configured[dev]) {
         cudaFuncSetAttribute(eik_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(eik_pipe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured = smem;
+        if (dev >= 0 && dev < 64) configured[dev] = smem;
     }
     const int n_tasks = (b.n_items * b.nz + 31) / 32;
     // per-warp global window: the scratch was sized for max_warps warps of the generic kernel
@@ -524,8 +524,16 @@ cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream)
+const char* eik_kernel_name(int which)
 {
+    static const char* names[kEikKernels] = {"eik_generic_kernel", "eik_fast_kernel", "eik_pipe_kernel", "eik_fine_kernel"};
+    return (which >= 0 && which < kEikKernels) ? names[which] : "?";
+}
+
+cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream, int* which)
+{
+    int dummy;
+    if (!which) which = &dummy;
     static int force_generic = -1;
     if (force_generic < 0) {
         const char* e = getenv("MCMCEQ_EIKONAL");
@@ -542,10 +550,12 @@ cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream)
         if ((long)(have / fast_scratch_floats_per_warp(D)) >= (long)sms * kPipeWarps && n_tasks >= (long)sms * kPipeWarps &&
             sms <= kPipeMaxCtas) {
             EikBatch piped = b;
+            *which = kEikPipe;
             return eik_launch_pipe(piped, b.task_counter, stream);
         }
     }
-    if (!force_generic && eik_fast_supported(b.nxmod, b.nz)) return eik_launch_fast(b, stream);
+    if (!force_generic && eik_fast_supported(b.nxmod, b.nz)) { *which = kEikFast; return eik_launch_fast(b, stream); }
+    *which = kEikGeneric;
     return eik_launch_generic(b, stream);
 }
 

@@ -57,8 +57,12 @@ cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream);
 bool eik_pipe_supported(int nxmod, int nz);
 size_t eik_pipe_tie_floats();
 cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t stream);
-// Picks the fast kernel when the grid allows it (MCMCEQ_EIKONAL=generic forces the generic one).
-cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream);
+// Picks the kernel: pipelined when the launch fills the GPU and the plane fits a shared-memory slice, fused for smaller
+// launches of such planes, generic otherwise (MCMCEQ_EIKONAL=generic forces the generic one).  *which (may be nullptr)
+// receives the kernel taken, for mq_profile_kernels.
+enum { kEikGeneric = 0, kEikFast = 1, kEikPipe = 2, kEikFine = 3, kEikKernels = 4 };
+const char* eik_kernel_name(int which);
+cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream, int* which = nullptr);
 // Regrouping of the solves of a table-mode batch (see EikBatch::order).  `work` holds the sort buffers:
 // eik_order_bytes(max_solves) bytes.  Fills order[0 .. round_up(max_solves, 32)).
 size_t eik_order_bytes(int max_solves);

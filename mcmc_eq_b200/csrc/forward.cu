@@ -90,8 +90,11 @@ cudaError_t launch_rasterise(Handle* h, const EvalView& v, int max_items)
 // ---- timing of the eikonal launches (mq_profile) -------------------------------------------
 struct Profile {
     std::vector<cudaEvent_t> ev;   // start/stop pairs not yet read
+    std::vector<int> which;        // kernel each pair's launch took (eikonal.cuh: kEik*)
     double ms_total = 0;
     long launches = 0;
+    double ms_by[kEikKernels] = {0, 0, 0, 0};
+    long n_by[kEikKernels] = {0, 0, 0, 0};
     bool enabled = false;
 };
 
@@ -110,13 +113,25 @@ void profile_collect(Handle* h, double* ms, long* launches, bool reset)
         cudaEventElapsedTime(&t, p->ev[i], p->ev[i + 1]);
         p->ms_total += t;
         p->launches++;
+        const int w = p->which[i / 2];
+        p->ms_by[w] += t;
+        p->n_by[w]++;
         cudaEventDestroy(p->ev[i]);
         cudaEventDestroy(p->ev[i + 1]);
     }
     p->ev.clear();
+    p->which.clear();
     *ms = p->ms_total;
     *launches = p->launches;
-    if (reset) { p->ms_total = 0; p->launches = 0; }
+    if (reset) {
+        p->ms_total = 0; p->launches = 0;
+        for (int k = 0; k < kEikKernels; k++) { p->ms_by[k] = 0; p->n_by[k] = 0; }
+    }
+}
+void profile_by_kernel(Handle* h, double* ms, long* launches)
+{
+    Profile* p = (Profile*)h->prof;
+    for (int k = 0; k < kEikKernels; k++) { ms[k] = p ? p->ms_by[k] : 0.0; launches[k] = p ? p->n_by[k] : 0; }
 }
 void profile_destroy(Handle* h)
 {
@@ -132,10 +147,11 @@ cudaError_t launch_tables(Handle* h, int max_items)
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, h->stream);
     }
+    int which = kEikGeneric;
     struct Stop {
-        Profile* pr; cudaEvent_t e0, e1; cudaStream_t s;
-        ~Stop() { if (e0) { cudaEventRecord(e1, s); pr->ev.push_back(e0); pr->ev.push_back(e1); } }
-    } stop{pr, e0, e1, h->stream};
+        Profile* pr; cudaEvent_t e0, e1; cudaStream_t s; int* which;
+        ~Stop() { if (e0) { cudaEventRecord(e1, s); pr->ev.push_back(e0); pr->ev.push_back(e1); pr->which.push_back(*which); } }
+    } stop{pr, e0, e1, h->stream, &which};
     EikBatch b = {};
     b.nxmod = h->nxmod; b.nz = h->nz;
     b.slow = h->slow; b.n_items = max_items; b.n_items_dev = h->n_items;
@@ -148,7 +164,7 @@ cudaError_t launch_tables(Handle* h, int max_items)
         b.order = h->eik_order;
     }
     b.task_counter = h->eik_task_counter; b.tie_scratch = h->eik_tie_scratch;
-    return eik_launch(b, h->stream);
+    return eik_launch(b, h->stream, &which);
 }
 
 // ---- travel-time lookup -------------------------------------------------------------------
@@ -217,7 +233,15 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // ---- residuals / origin time / class sums --------------------------------------------------
-// One warp per (chain, event): lanes stride over the event's picks (P first, then S).
+// One warp per (chain, event): lanes stride over the event's picks (P first, then S).  The event's residuals never leave
+// the register file: lane l keeps the raw residuals of picks l, l + 32, ... (KMAX of them; an event of config 3 / 4 has
+// 100 / 200 picks = 4 / 7 per lane) and their class codes packed four bits each, takes part in the warp sum that gives
+// the origin time (src/misfit.c:121-123), de-means its own and adds the squares to the eight class sums
+// (src/misfit.c:146-153), which live in a per-warp strip of shared memory indexed by class (one read-modify-write per
+// pick instead of eight selects).  Per-pick values reach HBM only when mq_get_predictions asks for them (want_pred).
+// Events with more than 32 * KMAX picks take the same kernel with the residuals in a global scratch (KMAX == 0).
+// With a power-of-two grid spacing every bilinear prefactor 1 / ((x2-x1)(y2-y1)) is a power of two, so the reference's
+// double product (src/interpol.c:80) equals a float product bit for bit and no FP64 instruction is issued.
 struct MisfitParams {
     int n, ne, ns, np, nz, nxmod, xp, md;
     float hgrid, z0, rh;
@@ -234,10 +258,14 @@ struct MisfitParams {
     int32_t* err;
 };
 
-__global__ void __launch_bounds__(128, 8) misfit_kernel(MisfitParams p)
+constexpr int kMisfitWarps = 4;
+
+template <int KMAX, bool POW2>
+__global__ void __launch_bounds__(kMisfitWarps * 32, (KMAX > 4 ? 6 : 8)) misfit_kernel(MisfitParams p)
 {
-    const int lane = threadIdx.x & 31;
-    const long task = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ float class_acc[kMisfitWarps][8][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long task = (long)blockIdx.x * kMisfitWarps + wib;
     if (task >= (long)p.n * p.ne) return;
     const int c = (int)(task / p.ne), e = (int)(task - (long)c * p.ne);
     if (p.v.hold && p.v.hold[c] != 0) return;
@@ -258,7 +286,7 @@ __global__ void __launch_bounds__(128, 8) misfit_kernel(MisfitParams p)
     const float* tabP = p.tab + (((size_t)p.v.tbuf[2 * c] * p.n + c) * 2 + 0) * p.tab_stride;
     const float* tabS = p.tab + (((size_t)p.v.tbuf[2 * c + 1] * p.n + c) * 2 + 1) * p.tab_stride;
     const size_t rowsz = (size_t)p.nz * p.xp;
-    float* resid = p.resid + (size_t)c * p.np;
+    float* resid = (KMAX == 0 || p.tpred) ? p.resid + (size_t)c * p.np : nullptr;
 
     // straight-ray branch (eikonal == 0, src/misfit.c:90,108): velocity of the nucleus nearest to z = 0
     float v0p = 1.f, v0s = 1.f;
@@ -279,11 +307,17 @@ __global__ void __launch_bounds__(128, 8) misfit_kernel(MisfitParams p)
     BilinearZ wz;
     if (p.eikonal != 0) wz = bilinear_depth(ez, p.hgrid, p.z0, p.nz);
     else { wz.iz1 = 0; wz.c = wz.d = wz.dyf = 0.f; wz.pref0 = 0.0; wz.oob = false; }
+    const float pref0f = (float)wz.pref0;     // exact when the spacing is a power of two
     const size_t zoff = (size_t)(wz.oob ? 0 : wz.iz1) * p.xp;
+    const float* tabPz = tabP + zoff;
+    const float* tabSz = tabS + zoff;
     float sum = 0.f;
     bool oob = false;         // a pick fell outside the table (1e30 sentinel of src/interpol.c:64-65)
-    unsigned present = 0u;    // classes that occur in this event
-    for (int j = b + lane; j < end; j += 32) {
+    constexpr int KR = KMAX > 0 ? KMAX : 1;
+    float rres[KR];           // raw residuals of this lane's picks
+    unsigned cps = 0u;        // their class codes 2*class + phase, four bits each (KMAX <= 8)
+
+    auto one_pick = [&](int j) -> float {
         const bool isS = (j - b) >= npk;
         const float dx = __fsub_rn(p.pk.x[j], ex), dy = __fsub_rn(p.pk.y[j], ey);
         const float dist = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
@@ -291,10 +325,30 @@ __global__ void __launch_bounds__(128, 8) misfit_kernel(MisfitParams p)
         if (p.eikonal == 0) {
             const float r2 = __fadd_rn(__fmul_rn(dist, dist), __fmul_rn(ez, ez));
             tt = (float)(sqrt((double)r2) / (double)(isS ? v0s : v0p));
+        } else if (POW2) {
+            // x1 = m1*h, x2 = (m1+1)*h and their difference are exact: the prefactor is 1/(h*h), a power of two
+            const int m1 = (int)__fmul_rn(dist, p.rh);
+            const bool out = wz.oob || m1 >= p.nxmod - 1;
+            oob = oob || out;
+            const float x1 = __fmul_rn((float)m1, p.hgrid), x2 = __fmul_rn((float)(m1 + 1), p.hgrid);
+            const float wa = __fsub_rn(x2, dist), wb = __fsub_rn(dist, x1);
+            const float* row = (isS ? tabSz : tabPz) + (size_t)p.pk.r0[j] * rowsz + (out ? 0 : m1);
+            float t12[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const float* q = row + (size_t)r * rowsz;
+                const float v1 = __ldg(q), v2 = __ldg(q + 1), v3 = __ldg(q + p.xp), v4 = __ldg(q + p.xp + 1);
+                float s4 = __fmul_rn(__fmul_rn(v1, wa), wz.c);
+                s4 = __fadd_rn(s4, __fmul_rn(__fmul_rn(v2, wb), wz.c));
+                s4 = __fadd_rn(s4, __fmul_rn(__fmul_rn(v3, wa), wz.d));
+                s4 = __fadd_rn(s4, __fmul_rn(__fmul_rn(v4, wb), wz.d));
+                t12[r] = out ? 1e30f : __fmul_rn(pref0f, s4);
+            }
+            tt = __fadd_rn(__fmul_rn(t12[0], p.pk.w1[j]), __fmul_rn(t12[1], p.pk.w2[j]));
         } else {
-            const BilinearX w = bilinear_dist(wz, dist, p.hgrid, p.rh, p.h_pow2 != 0, p.nxmod);
+            const BilinearX w = bilinear_dist(wz, dist, p.hgrid, p.rh, false, p.nxmod);
             oob = oob || w.oob;
-            const float* row = (isS ? tabS : tabP) + (size_t)p.pk.r0[j] * rowsz + zoff;
+            const float* row = (isS ? tabSz : tabPz) + (size_t)p.pk.r0[j] * rowsz;
             const float t1 = w.oob ? 1e30f : bilinear_eval(wz, w, row, p.xp);
             const float t2 = w.oob ? 1e30f : bilinear_eval(wz, w, row + rowsz, p.xp);
             tt = __fadd_rn(__fmul_rn(t1, p.pk.w1[j]), __fmul_rn(t2, p.pk.w2[j]));
@@ -306,33 +360,64 @@ __global__ void __launch_bounds__(128, 8) misfit_kernel(MisfitParams p)
             if (p.scor_flag <= 0) corr = (st == ridx) ? __fadd_rn(corr, d1) : __fsub_rn(corr, __fdiv_rn(d1, nsm1));
             if (p.scor_flag != 0 && st == ridx) corr = __fadd_rn(corr, d2);
         }
-        if (corr < -1000.f) atomicExch(p.err, MQ_ERR_STATCOR);
+        if (corr < -1000.f) atomicOr(p.err, kErrStatcor);
         tt = __fadd_rn(tt, corr);
-        const float diff = __fsub_rn(tt, p.pk.t[j]);
-        resid[j] = diff;
         if (p.tpred) p.tpred[(size_t)c * p.np + j] = tt;
-        sum += diff;
+        return __fsub_rn(tt, p.pk.t[j]);
+    };
+
+    if (KMAX > 0) {
+#pragma unroll
+        for (int i = 0; i < KR; i++) {
+            const int j = b + lane + 32 * i;
+            rres[i] = 0.f;
+            if (j < end) {
+                rres[i] = one_pick(j);
+                sum += rres[i];
+                cps |= (unsigned)p.pk.cp[j] << (4 * i);
+            }
+        }
+    } else {
+        for (int j = b + lane; j < end; j += 32) {
+            const float diff = one_pick(j);
+            resid[j] = diff;
+            sum += diff;
+        }
     }
     sum = warp_sum(sum);
     const float mean = sum / (float)(end - b);
     __syncwarp();
 
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j = b + lane; j < end; j += 32) {
-        const float d = __fsub_rn(resid[j], mean);
-        if (p.tpred) resid[j] = d;
-        const float d2 = d * d;
-        const int cp = p.pk.cp[j];
-        present |= 1u << cp;
+    float* acc_l = &class_acc[wib][0][lane];
 #pragma unroll
-        for (int k = 0; k < 8; k++) acc[k] += (cp == k) ? d2 : 0.f;
+    for (int k = 0; k < 8; k++) acc_l[k * 32] = 0.f;
+    if (KMAX > 0) {
+#pragma unroll
+        for (int i = 0; i < KR; i++) {
+            const int j = b + lane + 32 * i;
+            if (j < end) {
+                const float d = __fsub_rn(rres[i], mean);
+                if (p.tpred) resid[j] = d;
+                const int cp = (cps >> (4 * i)) & 15;
+                acc_l[cp * 32] += d * d;
+            }
+        }
+    } else {
+        for (int j = b + lane; j < end; j += 32) {
+            const float d = __fsub_rn(resid[j], mean);
+            if (p.tpred) resid[j] = d;
+            acc_l[p.pk.cp[j] * 32] += d * d;
+        }
     }
+    float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = warp_sum(acc[k]);
+    for (int k = 0; k < 8; k++) acc[k] = warp_sum(acc_l[k * 32]);
     // With a 1e30 prediction in the event every de-meaned residual of it is ~1e29 or more and its
     // square overflows FP32 in the reference: the event's classes get an infinite misfit.  Stated
     // explicitly here because the overflow would otherwise depend on the summation order.
     if (__any_sync(0xffffffffu, oob)) {
+        unsigned present = 0u;    // classes that occur in this event
+        for (int j = b + lane; j < end; j += 32) present |= 1u << p.pk.cp[j];
         present = __reduce_or_sync(0xffffffffu, present);
 #pragma unroll
         for (int k = 0; k < 8; k++) if (present & (1u << k)) acc[k] = __int_as_float(0x7f800000);
@@ -361,8 +446,23 @@ cudaError_t launch_misfit(Handle* h, const EvalView& v)
     p.eq = h->eq; p.pres = h->pres; p.sres = h->sres; p.tab = h->tab; p.evsum = h->evsum; p.origin = h->origin;
     p.evq = h->evq; p.oq = h->oq; p.resid = h->resid; p.tpred = h->want_pred ? h->tpred : nullptr; p.err = h->err;
     const long tasks = (long)h->n * h->ne;
-    const int wpb = 4;
-    misfit_kernel<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(p);
+    const unsigned grid = (unsigned)((tasks + kMisfitWarps - 1) / kMisfitWarps);
+    const int per_lane = (h->pk.max_event_picks + 31) / 32;
+    // the per-pick scratch exists when an event is too large for the register path or predictions are wanted
+    if ((per_lane > 8 || h->want_pred) && !h->resid) {
+        const cudaError_t e = cudaMalloc(&h->resid, (size_t)h->n * h->np * sizeof(float));
+        if (e != cudaSuccess) return e;
+        p.resid = h->resid;
+    }
+#define MISFIT_LAUNCH(K)                                                                               \
+    do {                                                                                               \
+        if (p.h_pow2) misfit_kernel<K, true><<<grid, kMisfitWarps * 32, 0, h->stream>>>(p);            \
+        else misfit_kernel<K, false><<<grid, kMisfitWarps * 32, 0, h->stream>>>(p);                    \
+    } while (0)
+    if (per_lane <= 4) MISFIT_LAUNCH(4);
+    else if (per_lane <= 8) MISFIT_LAUNCH(8);
+    else MISFIT_LAUNCH(0);
+#undef MISFIT_LAUNCH
     count_launch();
     return cudaGetLastError();
 }

@@ -19,5 +19,7 @@ cudaError_t launch_totals(Handle* h, const EvalView& v);
 void profile_enable(Handle* h, bool on);
 void profile_collect(Handle* h, double* ms, long* launches, bool reset);
 void profile_destroy(Handle* h);
+// time and launches per eikonal kernel (indices kEik* of eikonal.cuh) of the accumulation profile_collect last read
+void profile_by_kernel(Handle* h, double* ms, long* launches);
 
 }  // namespace mq

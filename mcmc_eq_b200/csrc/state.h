@@ -21,6 +21,10 @@
 
 namespace mq {
 
+// bits of the device error word Handle::err
+constexpr int kErrStatcor = 1;   // a pick points to a station correction < -1000 (the reference exit()s, src/misfit.c:93,111)
+constexpr int kErrRetry = 2;     // a start value could not be drawn inside its bounds (mq_init_chains)
+
 struct DevPicks {
     int n_events, n_picks, max_event_picks;
     int32_t* ev_off;   // [ne+1]
@@ -87,14 +91,19 @@ struct Handle {
     float *evsum, *origin;
     float* mf;           // [n][8]
     double *ll, *rms, *misfit;
-    int32_t* err;        // [1] device error flag (invalid station correction etc.)
+    int32_t* err;        // [1] device error word (bits kErrStatcor, kErrRetry)
+    int32_t* host_flags; // pinned [2]: copies of err and solve_status made at the end of an asynchronous call ...
+    cudaEvent_t flags_ev; // ... valid once this event has completed
+    bool flags_pending;
+    cudaEvent_t timer_ev[2][16];   // mq_timer
+    int eik_pipe_smem;   // dynamic shared memory eik_pipe_kernel has been opted in for on this handle's device
 
     // evaluation plumbing
     EvalView cur_view;   // view of the current state
     EvalView prop_view;  // view of the proposal (mq_step)
     float *evq, *oq;     // [n][8], [n] single-event results
     float* mf_eval;      // [n][8] totals of the last evaluation
-    float* resid;        // [n][np] raw residual scratch / de-meaned residuals of the last evaluation
+    float* resid;        // [n][np] per-pick scratch, or nullptr: allocated when predictions are wanted or an event has more than 256 picks
     float* tpred;        // [n][np] or nullptr (allocated on first mq_get_predictions)
     bool want_pred;
 
@@ -115,6 +124,7 @@ struct Handle {
 
     // sampler (chain.cu)
     void* sampler;
+    int ring_slots;      // records per chain of the device-side output ring (mq_set_ring; 0 = default)
 
     // optional timing of the dominant kernel (mq_profile): CUDA events round every eikonal launch
     void* prof;

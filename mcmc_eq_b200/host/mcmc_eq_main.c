@@ -15,8 +15,15 @@
  * otherwise /dev/urandom (src/mcmc_eq.c:250-265,393-394).  -s overrides.  The random streams are this
  * library's counter-based generator, not libc rand(): chains are statistically, not bitwise, the reference's.
  *
+ * Output path: decimated records wait in a device-side ring (-r slots per chain, default 4); after every chunk of
+ * iterations the main thread starts an asynchronous drain (mq_drain_begin: pack kernel + device-to-host copy on a second
+ * stream) and goes on stepping, a writer thread waits for the batch and formats the print_model_raw text
+ * (src/mcmc_eq.c:234-248) into the per-chain files.  The reference writes and flushes each record from inside the
+ * sampling loop (:1163).
+ *
  * Unlike the reference (which exit(0)s on every error) the exit status is non-zero on failure.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -99,6 +106,60 @@ static int apply_model_dat(const mq_config* cfg, mq_models* m, FILE* log)
     return 0;
 }
 
+/* ---- writer thread: takes begun batches from a two-deep queue, waits for their records, writes them ----------------- */
+typedef struct {
+    pthread_t thread;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    mq_batch* q[2];
+    int n_q, stop, failed;
+    long lost, records;
+    sink_t* sink;
+} writer_t;
+
+static void* writer_main(void* arg)
+{
+    writer_t* w = (writer_t*)arg;
+    for (;;) {
+        mq_batch* b;
+        int n = 0, lost = 0;
+        pthread_mutex_lock(&w->mu);
+        while (w->n_q == 0 && !w->stop) pthread_cond_wait(&w->cv, &w->mu);
+        if (w->n_q == 0) { pthread_mutex_unlock(&w->mu); return NULL; }
+        b = w->q[0];
+        pthread_mutex_unlock(&w->mu);
+        if (mq_batch_wait(b, &n, &lost) != MQ_OK || mq_batch_deliver(b, write_record, w->sink) != MQ_OK) w->failed = 1;
+        mq_batch_release(b);
+        pthread_mutex_lock(&w->mu);
+        w->q[0] = w->q[1]; w->n_q--;
+        w->lost += lost; w->records += n;
+        pthread_cond_broadcast(&w->cv);
+        pthread_mutex_unlock(&w->mu);
+    }
+}
+
+static void writer_wait_slot(writer_t* w)             /* until one of the handle's two batches is free again */
+{
+    pthread_mutex_lock(&w->mu);
+    while (w->n_q == 2) pthread_cond_wait(&w->cv, &w->mu);
+    pthread_mutex_unlock(&w->mu);
+}
+
+static void writer_push(writer_t* w, mq_batch* b)
+{
+    pthread_mutex_lock(&w->mu);
+    w->q[w->n_q++] = b;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
+}
+
+static void writer_idle(writer_t* w)                  /* until everything pushed so far is on disk */
+{
+    pthread_mutex_lock(&w->mu);
+    while (w->n_q > 0) pthread_cond_wait(&w->cv, &w->mu);
+    pthread_mutex_unlock(&w->mu);
+}
+
 static unsigned long urandom_seed(void)
 {
     unsigned long v = (unsigned long)time(NULL);
@@ -125,7 +186,8 @@ static void out_name(char* dst, size_t cap, const char* pattern, int n_chains, i
 
 int main(int argc, char** argv)
 {
-    int rc = 0, n_chains = 1, device = 0, quiet = 0, i, c, from_file = 0;
+    int rc = 0, n_chains = 1, device = 0, quiet = 0, i, c, from_file = 0, ring = 0, writer_on = 0;
+    writer_t wr;
     long seed_arg = -1;
     mq_config cfg;
     mqio_picks pk;
@@ -139,8 +201,9 @@ int main(int argc, char** argv)
 
     memset(&pk, 0, sizeof pk);
     memset(&sink, 0, sizeof sink);
+    memset(&wr, 0, sizeof wr);
     if (argc < 4) {
-        fprintf(stderr, "usage: %s config_eqx.dat outfile picks [-n chains] [-d device] [-s seed] [-q]\n", argv[0]);
+        fprintf(stderr, "usage: %s config_eqx.dat outfile picks [-n chains] [-d device] [-s seed] [-r ring slots] [-q]\n", argv[0]);
         return 2;
     }
     if ((env = getenv("MCMCEQ_CHAINS")) != NULL) n_chains = atoi(env);
@@ -149,6 +212,7 @@ int main(int argc, char** argv)
         if (!strcmp(argv[i], "-n") && i + 1 < argc) n_chains = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) seed_arg = atol(argv[++i]);
+        else if (!strcmp(argv[i], "-r") && i + 1 < argc) ring = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-q")) quiet = 1;
         /* anything else is ignored, as the reference ignores extra arguments */
     }
@@ -164,6 +228,7 @@ int main(int argc, char** argv)
         if (!quiet) fprintf(stderr, "%d chain(s) on device %d, seed %lu, %d events, %d stations, %d picks\n", n_chains, device, seed,
                             pk.view.n_events, pk.view.n_stations, pk.view.n_picks);
         MQ(mq_create(&cfg, &pk.view, n_chains, device, (uint64_t)seed, &h));
+        if (ring > 0) MQ(mq_set_ring(h, ring));
     }
 
     sink.n_chains = n_chains;
@@ -209,20 +274,33 @@ int main(int argc, char** argv)
         for (c = 0; c < n_chains && c < 10; c++)
             fprintf(stderr, "Start model found with loglikelihood %f RMS=%f\n", ll[c], rms[c]);
     }
-    for (c = 0; c < n_chains; c++) MQ(mq_snapshot(h, c, 0, write_record, &sink));
+    MQ(mq_snapshot_all(h, 0, write_record, &sink));
 
-    /* main loop (src/mcmc_eq.c:845-1192): the chain ends after j_max_start + j_max_main ACCEPTED models.  Each
-     * chain holds one pending decimated record, so the records are drained at least every `deci` iterations. */
+    /* main loop (src/mcmc_eq.c:845-1192): the chain ends after j_max_start + j_max_main ACCEPTED models.  A chain's
+     * ring holds `ring` decimated records (at most one per deci iterations), so a chunk of ring/2 * deci iterations
+     * between two drains loses nothing even with one drain still in flight. */
     {
         const long target = (long)cfg.j_max_start + (long)cfg.j_max_main;
-        int chunk = cfg.deci > 0 ? cfg.deci : 1000;
-        if (chunk > 2000) chunk = 2000;
+        const int slots = ring > 0 ? ring : 4;
+        long chunk_l = (cfg.deci > 0 ? (long)cfg.deci : 1000L) * (slots > 1 ? slots / 2 : 1);
+        int chunk;
+        if (chunk_l > 2000) chunk_l = 2000;
+        if (cfg.deci > 0 && chunk_l < cfg.deci && cfg.deci <= 2000) chunk_l = cfg.deci;
+        chunk = (int)chunk_l;
+        wr.sink = &sink;
+        pthread_mutex_init(&wr.mu, NULL);
+        pthread_cond_init(&wr.cv, NULL);
+        if (pthread_create(&wr.thread, NULL, writer_main, &wr) != 0) FAIL("could not start the writer thread");
+        writer_on = 1;
         for (;;) {
-            int lost = 0, running = 0;
+            int running = 0;
+            mq_batch* b = NULL;
             MQ(mq_step(h, chunk, NULL));
             iters_done += chunk;
-            MQ(mq_drain(h, write_record, &sink, &lost));
-            if (lost) fprintf(stderr, "warning: %d decimated record(s) were overwritten before being written\n", lost);
+            writer_wait_slot(&wr);
+            MQ(mq_drain_begin(h, &b));        /* returns at once; the next chunk runs next to the copy */
+            writer_push(&wr, b);
+            if (wr.failed) FAIL("writing records failed: %s", mq_last_error());
             MQ(mq_get_stats(h, counts, ll, rms));
             for (c = 0; c < n_chains; c++)
                 if (counts[20 * c + 17] < target) running++;
@@ -237,12 +315,19 @@ int main(int argc, char** argv)
     }
 
     /* best model and diagnostics (src/mcmc_eq.c:1196-1207) */
-    for (c = 0; c < n_chains; c++) {
-        MQ(mq_snapshot(h, c, 1, write_record, &sink));
-        mqio_write_counts(sink.out[c], counts + 20 * c);
-    }
+    writer_idle(&wr);
+    if (wr.lost) fprintf(stderr, "warning: %ld decimated record(s) were dropped because a chain's ring was full (-r)\n", wr.lost);
+    MQ(mq_snapshot_all(h, 1, write_record, &sink));
+    for (c = 0; c < n_chains; c++) mqio_write_counts(sink.out[c], counts + 20 * c);
 
 done:
+    if (writer_on) {
+        pthread_mutex_lock(&wr.mu);
+        wr.stop = 1;
+        pthread_cond_broadcast(&wr.cv);
+        pthread_mutex_unlock(&wr.mu);
+        pthread_join(wr.thread, NULL);
+    }
     if (sink.out)
         for (c = 0; c < n_chains; c++)
             if (sink.out[c]) fclose(sink.out[c]);

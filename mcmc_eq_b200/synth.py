@@ -90,5 +90,6 @@ def workload(n_events: int = 200, n_stations: int = 50, seed: int = 33, device: 
     sigma = rms * ((cls + 1 + 2.5 * is_s) / 4.0) * 2.0
     t = np.round(tpred.astype(np.float64) + geo["rng"].normal(0, 1, tpred.shape) * sigma, 3)   # pick files carry 3 decimals
     pk = picks_from(geo, t.astype(np.float32))
-    truth = dict(z=TRUTH_Z, vp=TRUTH_VP, vpvs=TRUTH_VPVS, eq=geo["ev"], pres=geo["pcor"], sres=geo["scor"], t64=t)
+    truth = dict(z=TRUTH_Z, vp=TRUTH_VP, vpvs=TRUTH_VPVS, eq=geo["ev"], pres=geo["pcor"], sres=geo["scor"], t64=t,
+                 tpred=np.asarray(tpred, np.float32))      # noise-free predictions the picks were made from
     return cfg, pk, truth
