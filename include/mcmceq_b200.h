@@ -129,6 +129,14 @@ int mq_time_2d(const float* hs, float* t, int nx, int ny, float xs, float ys, fl
 int mq_eikonal_batch(const float* slow, const int32_t* src_iz, int n, int nxmod, int nz, float* t_out,
                      int32_t* status, int device);
 
+/* Drop-in for   float traveltimet(float **ttt, int nx, int ny, int nz, float h, float dist, float z, float z0)
+ * (reference src/interpol.c:43-83): bilinear interpolation of one receiver layer of a HOST table, ttt[iz][ix] with
+ * iz the source-depth node and ix the distance node (nx, ny are the grid's horizontal node counts, the table has
+ * (int)sqrt(nx^2 + ny^2) distance nodes, :52); 1e30 outside the table (:64-65).  The four corner values travel to
+ * the device and the library's own lookup code (the one misfit_kernel uses for every pick) evaluates them, so this
+ * entry point is the unit-testable twin of that code, not a second implementation.  *t_out receives the time. */
+int mq_traveltimet(float* const* ttt, int nx, int ny, int nz, float h, float dist, float z, float z0, float* t_out, int device);
+
 /* ===== batched sampler ==================================================================
  * One handle drives n_chains chains on one GPU.  Model state, travel-time tables and RNG
  * state stay on the device between calls. */
@@ -156,6 +164,10 @@ int mq_forward_host(mq_handle* h, const mq_models* m, int calct, float* mf, floa
  * :1171), as device-to-device copies.  Not needed with mq_step, which flips buffers instead. */
 int mq_tables_save(mq_handle* h);
 int mq_tables_restore(mq_handle* h);
+/* The same for the tables of one phase only: phases = 1 (P), 2 (S) or 3 (both).  A 'V' proposal rebuilds the S table
+ * alone (calct = 2, src/mcmc_eq.c:975) while the P table stays. */
+int mq_tables_save_phases(mq_handle* h, int phases);
+int mq_tables_restore_phases(mq_handle* h, int phases);
 
 /* Full travel-time table of one chain in the reference layout ttt[nz][nz][nxmod]
  * (ttt[j][iz][i], src/misfit.c:281-288); phase 1 = P, 2 = S.  Recomputes that chain's table
@@ -308,6 +320,8 @@ int mq_profile(mq_handle* h, int enable, double* eikonal_ms, int64_t* eikonal_la
 #define MQ_EIK_KERNELS 4
 int mq_profile_kernels(mq_handle* h, int64_t* launches, double* ms);
 const char* mq_eikonal_kernel_name(int k);
+/* The same accumulation for the lookup / residual kernel (misfit_kernel): launches and their summed device time. */
+int mq_profile_misfit(mq_handle* h, int64_t* launches, double* ms);
 
 /* CUDA-event stopwatch on the handle's stream: stop = 0 records the start of `slot` (0..15), stop = 1 records
  * the end, waits for it and returns the device time between the two in *elapsed_ms. */

@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
         L.mq_snapshot.argtypes = [C.c_void_p, C.c_int, C.c_int, RECORD_FN, C.c_void_p]
         L.mq_snapshot_all.argtypes = [C.c_void_p, C.c_int, RECORD_FN, C.c_void_p]
         L.mq_profile_kernels.argtypes = [C.c_void_p, lp, dp]
+        L.mq_profile_misfit.argtypes = [C.c_void_p, lp, dp]
         L.mq_eikonal_kernel_name.argtypes = [C.c_int]
         L.mq_eikonal_kernel_name.restype = C.c_char_p
         L.mq_sync.argtypes = [C.c_void_p]
@@ -459,6 +460,12 @@ class Sampler:
 
     def snapshot_all(self, which: int = 0):
         return self._collect(lambda fn: check(lib().mq_snapshot_all(self.h, which, fn, None)))
+
+    def profile_misfit(self):
+        """(launches, ms) of the misfit kernel over the accumulation the last profile() call read."""
+        n, ms = C.c_int64(0), C.c_double(0)
+        check(lib().mq_profile_misfit(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
 
     def profile_kernels(self):
         """{kernel name: (launches, ms)} of the eikonal launches counted by the last profile() call."""

@@ -79,9 +79,9 @@ def build_host(force: bool = False) -> None:
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_cuda(force, verbose)
+    build_host(force)          # before the oracle: oracle/_ref links the reference's drivers against the function-seam shim
     build_oracle(force)
     build_emu(force)
-    build_host(force)
 
 
 if __name__ == "__main__":

@@ -443,19 +443,47 @@ extern "C" int mq_forward_host(mq_handle* hh, const mq_models* m, int calct, flo
 // Host-driven use (a reference-style main that calls mq_forward_host per proposal): the device tables are those of
 // the last call with calct != 0.  The reference keeps a backup copy of its tables and restores it after a rejection
 // (src/mcmc_eq.c:856,1161,1171); these two calls are that backup / restore, device to device.
-static int tables_copy(mq_handle* hh, int from, int to, const char* who)
+static int tables_copy(mq_handle* hh, int from, int to, int phases, const char* who)
 {
-    if (!hh) { set_error("%s: null", who); return MQ_ERR_ARG; }
+    if (!hh || phases < 1 || phases > 3) { set_error("%s: bad argument", who); return MQ_ERR_ARG; }
     Handle* h = &hh->h;
     if (!h->models_set) { set_error("%s: no models", who); return MQ_ERR_STATE; }
     MQ_CUDA(cudaSetDevice(h->device));
     const size_t half = (size_t)h->n * 2 * h->tab_stride;
-    MQ_CUDA(cudaMemcpyAsync(h->tab + (size_t)to * half, h->tab + (size_t)from * half, half * sizeof(float), cudaMemcpyDeviceToDevice,
-                            h->stream));
+    if (phases == 3) {
+        MQ_CUDA(cudaMemcpyAsync(h->tab + (size_t)to * half, h->tab + (size_t)from * half, half * sizeof(float), cudaMemcpyDeviceToDevice,
+                                h->stream));
+        return MQ_OK;
+    }
+    // one phase of every chain: rows of tab_stride floats at a pitch of two tables
+    const size_t ph = phases == 1 ? 0 : 1, w = h->tab_stride * sizeof(float);
+    MQ_CUDA(cudaMemcpy2DAsync(h->tab + (size_t)to * half + ph * h->tab_stride, 2 * w, h->tab + (size_t)from * half + ph * h->tab_stride,
+                              2 * w, w, h->n, cudaMemcpyDeviceToDevice, h->stream));
     return MQ_OK;
 }
-extern "C" int mq_tables_save(mq_handle* hh) { return tables_copy(hh, 0, 1, "mq_tables_save"); }
-extern "C" int mq_tables_restore(mq_handle* hh) { return tables_copy(hh, 1, 0, "mq_tables_restore"); }
+extern "C" int mq_tables_save(mq_handle* hh) { return tables_copy(hh, 0, 1, 3, "mq_tables_save"); }
+extern "C" int mq_tables_restore(mq_handle* hh) { return tables_copy(hh, 1, 0, 3, "mq_tables_restore"); }
+extern "C" int mq_tables_save_phases(mq_handle* hh, int phases) { return tables_copy(hh, 0, 1, phases, "mq_tables_save_phases"); }
+extern "C" int mq_tables_restore_phases(mq_handle* hh, int phases) { return tables_copy(hh, 1, 0, phases, "mq_tables_restore_phases"); }
+
+extern "C" int mq_traveltimet(float* const* ttt, int nx, int ny, int nz, float h, float dist, float z, float z0, float* t_out, int device)
+{
+    // nx, ny are the grid's horizontal node counts: the distance axis has nxmod = (int)sqrt(nx^2 + ny^2) nodes (src/interpol.c:52)
+    if (!ttt || !t_out || nx < 1 || ny < 1 || nz < 2 || !(h > 0.f)) { set_error("mq_traveltimet: bad argument"); return MQ_ERR_ARG; }
+    const int nxmod = (int)sqrt((double)(nx * nx + ny * ny));
+    int iz1 = 0, m1 = 0;
+    if (!traveltimet_cell(dist, z, h, z0, nz, nxmod, &iz1, &m1) || iz1 < 0 || m1 < 0) { *t_out = 1e30f; return MQ_OK; }
+    MQ_CUDA(cudaSetDevice(device));
+    const float corners[4] = {ttt[iz1][m1], ttt[iz1][m1 + 1], ttt[iz1 + 1][m1], ttt[iz1 + 1][m1 + 1]};
+    float* d = nullptr;
+    MQ_CUDA(cudaMalloc(&d, 5 * sizeof(float)));
+    cudaError_t e = cudaMemcpy(d, corners, sizeof corners, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_traveltimet(dist, z, h, z0, nz, nxmod, d, d + 4, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(t_out, d + 4, sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    MQ_CUDA(e);
+    return MQ_OK;
+}
 
 extern "C" int mq_sync(mq_handle* hh)
 {
@@ -573,6 +601,15 @@ extern "C" int mq_profile_kernels(mq_handle* hh, int64_t* launches, double* ms)
     return MQ_OK;
 }
 extern "C" const char* mq_eikonal_kernel_name(int k) { return eik_kernel_name(k); }
+extern "C" int mq_profile_misfit(mq_handle* hh, int64_t* launches, double* ms)
+{
+    if (!hh) { set_error("mq_profile_misfit: null"); return MQ_ERR_ARG; }
+    double m = 0; long n = 0;
+    profile_misfit(&hh->h, &m, &n);
+    if (launches) *launches = n;
+    if (ms) *ms = m;
+    return MQ_OK;
+}
 
 // ---- device timers on the handle's stream (bench.py times K steps with these) ---------------------
 extern "C" int mq_timer(mq_handle* hh, int slot, int stop, double* elapsed_ms)

@@ -1345,9 +1345,16 @@ extern "C" int mq_batch_deliver(mq_batch* b, mq_record_fn fn, void* user)
     if (!b || !fn) { set_error("mq_batch_deliver: null"); return MQ_ERR_ARG; }
     if (b->state != 2) { const int rc = mq_batch_wait(b, nullptr, nullptr); if (rc != MQ_OK) return rc; }
     const Handle* h = b->h;
+    // the pack kernel places the chains in the order its blocks arrive; deliver by chain number (a chain's records are
+    // next to each other in the order they were produced, and the sort is stable)
+    std::vector<int> order((size_t)b->n_records);
+    for (int i = 0; i < b->n_records; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        return ((const int32_t*)(b->h_stage + (size_t)x * b->rec_floats))[0] < ((const int32_t*)(b->h_stage + (size_t)y * b->rec_floats))[0];
+    });
     for (int i = 0; i < b->n_records; i++) {
         mq_record r;
-        record_view(b->h_stage + (size_t)i * b->rec_floats, h->md, h->ne, h->ns, &r);
+        record_view(b->h_stage + (size_t)order[i] * b->rec_floats, h->md, h->ne, h->ns, &r);
         if (fn(user, &r)) break;
     }
     return MQ_OK;

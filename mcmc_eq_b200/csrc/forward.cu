@@ -8,6 +8,7 @@
 #include "launch_count.h"
 #include "tria.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace mq {
@@ -95,6 +96,9 @@ struct Profile {
     long launches = 0;
     double ms_by[kEikKernels] = {0, 0, 0, 0};
     long n_by[kEikKernels] = {0, 0, 0, 0};
+    std::vector<cudaEvent_t> mev;  // start/stop pairs round the misfit kernel
+    double misfit_ms = 0, misfit_ms_read = 0;
+    long misfit_n = 0, misfit_n_read = 0;
     bool enabled = false;
 };
 
@@ -121,12 +125,32 @@ void profile_collect(Handle* h, double* ms, long* launches, bool reset)
     }
     p->ev.clear();
     p->which.clear();
+    for (size_t i = 0; i + 1 < p->mev.size(); i += 2) {
+        float t = 0.f;
+        cudaEventSynchronize(p->mev[i + 1]);
+        cudaEventElapsedTime(&t, p->mev[i], p->mev[i + 1]);
+        p->misfit_ms += t;
+        p->misfit_n++;
+        cudaEventDestroy(p->mev[i]);
+        cudaEventDestroy(p->mev[i + 1]);
+    }
+    p->mev.clear();
     *ms = p->ms_total;
     *launches = p->launches;
     if (reset) {
         p->ms_total = 0; p->launches = 0;
         for (int k = 0; k < kEikKernels; k++) { p->ms_by[k] = 0; p->n_by[k] = 0; }
+        p->misfit_ms_read = p->misfit_ms; p->misfit_n_read = p->misfit_n;
+        p->misfit_ms = 0; p->misfit_n = 0;
+    } else {
+        p->misfit_ms_read = p->misfit_ms; p->misfit_n_read = p->misfit_n;
     }
+}
+void profile_misfit(Handle* h, double* ms, long* launches)
+{
+    Profile* p = (Profile*)h->prof;
+    *ms = p ? p->misfit_ms_read : 0.0;
+    *launches = p ? p->misfit_n_read : 0;
 }
 void profile_by_kernel(Handle* h, double* ms, long* launches)
 {
@@ -226,6 +250,34 @@ __device__ __forceinline__ float bilinear_eval(const BilinearZ& wz, const Biline
     return (float)(w.pref * (double)s);
 }
 
+// One lookup with the four corner values handed in (mq_traveltimet): corners = t[iz1][m1], t[iz1][m1+1], t[iz1+1][m1], t[iz1+1][m1+1]
+__global__ void traveltimet_kernel(float dist, float z, float hgrid, float z0, int nz, int nxmod, const float* corners, float* out)
+{
+    const BilinearZ wz = bilinear_depth(z, hgrid, z0, nz);
+    const BilinearX w = bilinear_dist(wz, dist, hgrid, 1.0f / hgrid, false, nxmod);
+    if (w.oob) { *out = 1e30f; return; }
+    BilinearX w0 = w;
+    w0.m1 = 0;
+    *out = bilinear_eval(wz, w0, corners, 2);
+}
+
+// cell the lookup of (dist, z) reads, computed on the host with the same float operations (src/interpol.c:56-63)
+bool traveltimet_cell(float dist, float z, float hgrid, float z0, int nz, int nxmod, int* iz1, int* m1)
+{
+    const float y = z - z0;
+    *iz1 = (int)(y / hgrid);
+    *m1 = (int)(dist / hgrid);
+    return !(*iz1 >= nz - 1 || *m1 >= nxmod - 1);
+}
+
+cudaError_t launch_traveltimet(float dist, float z, float hgrid, float z0, int nz, int nxmod, const float* d_corners, float* d_out,
+                               cudaStream_t s)
+{
+    traveltimet_kernel<<<1, 1, 0, s>>>(dist, z, hgrid, z0, nz, nxmod, d_corners, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -234,12 +286,12 @@ __device__ __forceinline__ float warp_sum(float v)
 
 // ---- residuals / origin time / class sums --------------------------------------------------
 // One warp per (chain, event): lanes stride over the event's picks (P first, then S).  The event's residuals never leave
-// the register file: lane l keeps the raw residuals of picks l, l + 32, ... (KMAX of them; an event of config 3 / 4 has
-// 100 / 200 picks = 4 / 7 per lane) and their class codes packed four bits each, takes part in the warp sum that gives
-// the origin time (src/misfit.c:121-123), de-means its own and adds the squares to the eight class sums
-// (src/misfit.c:146-153), which live in a per-warp strip of shared memory indexed by class (one read-modify-write per
-// pick instead of eight selects).  Per-pick values reach HBM only when mq_get_predictions asks for them (want_pred).
-// Events with more than 32 * KMAX picks take the same kernel with the residuals in a global scratch (KMAX == 0).
+// the SM: lane l keeps the raw residuals of picks l, l + 32, ... in its column of a per-warp strip of shared memory
+// (kMisfitKeep of them: an event of config 3 / 4 has 100 / 200 picks = 4 / 7 per lane), takes part in the warp sum that
+// gives the origin time (src/misfit.c:121-123), de-means its own and adds the squares to the eight class sums
+// (src/misfit.c:146-153), which live in a second strip indexed by class (one read-modify-write per pick instead of eight
+// selects).  Per-pick values reach HBM only when mq_get_predictions asks for them (want_pred).
+// Events with more than 32 * kMisfitKeep picks take the same kernel with the residuals in a global scratch (KEEP == false).
 // With a power-of-two grid spacing every bilinear prefactor 1 / ((x2-x1)(y2-y1)) is a power of two, so the reference's
 // double product (src/interpol.c:80) equals a float product bit for bit and no FP64 instruction is issued.
 struct MisfitParams {
@@ -259,11 +311,15 @@ struct MisfitParams {
 };
 
 constexpr int kMisfitWarps = 4;
+constexpr int kMisfitKeep = 8;      // residuals per lane kept in shared memory: events of up to 256 picks
 
-template <int KMAX, bool POW2>
-__global__ void __launch_bounds__(kMisfitWarps * 32, (KMAX > 4 ? 6 : 8)) misfit_kernel(MisfitParams p)
+// KEEP: residuals stay in shared memory; POW2: power-of-two grid spacing (float prefactor, no division); RAY: the
+// straight-ray branch eikonal == 0 (src/misfit.c:90,108) instead of the table lookup.
+template <bool KEEP, bool POW2, bool RAY>
+__global__ void __launch_bounds__(kMisfitWarps * 32, 8) misfit_kernel(MisfitParams p)
 {
     __shared__ float class_acc[kMisfitWarps][8][32];
+    __shared__ float res_keep[KEEP ? kMisfitWarps : 1][KEEP ? kMisfitKeep : 1][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long task = (long)blockIdx.x * kMisfitWarps + wib;
     if (task >= (long)p.n * p.ne) return;
@@ -276,21 +332,27 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, (KMAX > 4 ? 6 : 8)) misfit_
     if (p.v.q_idx[c] == e) { ex = p.v.q_xyz[3 * c]; ey = p.v.q_xyz[3 * c + 1]; ez = p.v.q_xyz[3 * c + 2]; }
     else { const float* q = p.eq + ((size_t)c * p.ne + e) * 3; ex = q[0]; ey = q[1]; ez = q[2]; }
 
+    // proposed station-correction perturbation (src/mcmc_eq.c:910-928), the same for every pick of the chain: the
+    // chosen station gets +d1 (and +d2 under a non-zero scor_flag), every other one -d1/(nos-1) when scor_flag <= 0
     const int ridx = p.v.r_idx[c];
-    const float* rd = p.v.r_d + 4 * (size_t)c;
-    const float nsm1 = (float)(p.ns - 1);
+    float rd1P = 0.f, rd1S = 0.f, rd2P = 0.f, rd2S = 0.f, rq1P = 0.f, rq1S = 0.f;
+    if (ridx >= 0) {
+        const float* rd = p.v.r_d + 4 * (size_t)c;
+        const float nsm1 = (float)(p.ns - 1);
+        rd1P = rd[0]; rd1S = rd[1]; rd2P = rd[2]; rd2S = rd[3];
+        rq1P = __fdiv_rn(rd1P, nsm1); rq1S = __fdiv_rn(rd1S, nsm1);
+    }
     const float* pres = (ridx == -2) ? p.v.pres_over + (size_t)c * p.ns : p.pres + (size_t)c * p.ns;
     const float* sres = (ridx == -2) ? p.v.sres_over + (size_t)c * p.ns : p.sres + (size_t)c * p.ns;
 
     const int b = p.pk.ev_off[e], end = p.pk.ev_off[e + 1], npk = p.pk.n_p[e];
-    const float* tabP = p.tab + (((size_t)p.v.tbuf[2 * c] * p.n + c) * 2 + 0) * p.tab_stride;
-    const float* tabS = p.tab + (((size_t)p.v.tbuf[2 * c + 1] * p.n + c) * 2 + 1) * p.tab_stride;
-    const size_t rowsz = (size_t)p.nz * p.xp;
-    float* resid = (KMAX == 0 || p.tpred) ? p.resid + (size_t)c * p.np : nullptr;
+    const int rowsz = p.nz * p.xp;      // a (chain, phase) table holds n_rows * nz * xp floats: 32-bit offsets inside it
+    float* resid = (!KEEP || p.tpred) ? p.resid + (size_t)c * p.np : nullptr;
 
-    // straight-ray branch (eikonal == 0, src/misfit.c:90,108): velocity of the nucleus nearest to z = 0
     float v0p = 1.f, v0s = 1.f;
-    if (p.eikonal == 0) {
+    BilinearZ wz;
+    wz.iz1 = 0; wz.c = wz.d = wz.dyf = 0.f; wz.pref0 = 0.0; wz.oob = false;
+    if (RAY) {   // velocity of the nucleus nearest to z = 0
         const int mb = p.v.mbuf[c];
         const size_t mo = ((size_t)mb * p.n + c) * p.md;
         const int d = p.dim[mb * p.n + c];
@@ -302,41 +364,40 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, (KMAX > 4 ? 6 : 8)) misfit_
         }
         v0p = p.vp[mo + k];
         v0s = __fdiv_rn(v0p, p.vpvs[mo + k]);
+    } else if (POW2) {   // depth part of the bilinear weights; y / h == y * (1/h) and every product below is exact
+        const float y = __fsub_rn(ez, p.z0);
+        wz.iz1 = (int)__fmul_rn(y, p.rh);
+        wz.oob = wz.iz1 >= p.nz - 1;
+        wz.c = __fsub_rn(__fmul_rn((float)(wz.iz1 + 1), p.hgrid), y);
+        wz.d = __fsub_rn(y, __fmul_rn((float)wz.iz1, p.hgrid));
+    } else {
+        wz = bilinear_depth(ez, p.hgrid, p.z0, p.nz);
     }
-
-    BilinearZ wz;
-    if (p.eikonal != 0) wz = bilinear_depth(ez, p.hgrid, p.z0, p.nz);
-    else { wz.iz1 = 0; wz.c = wz.d = wz.dyf = 0.f; wz.pref0 = 0.0; wz.oob = false; }
-    const float pref0f = (float)wz.pref0;     // exact when the spacing is a power of two
-    const size_t zoff = (size_t)(wz.oob ? 0 : wz.iz1) * p.xp;
-    const float* tabPz = tabP + zoff;
-    const float* tabSz = tabS + zoff;
+    const float pref0f = p.rh * p.rh;     // POW2: 1 / ((x2-x1)(y2-y1)) = 1/h^2 exactly (src/interpol.c:80)
+    const int zoff = (wz.oob ? 0 : wz.iz1) * p.xp;
+    const float* tabPz = p.tab + (((size_t)p.v.tbuf[2 * c] * p.n + c) * 2 + 0) * p.tab_stride + zoff;
+    const float* tabSz = p.tab + (((size_t)p.v.tbuf[2 * c + 1] * p.n + c) * 2 + 1) * p.tab_stride + zoff;
     float sum = 0.f;
     bool oob = false;         // a pick fell outside the table (1e30 sentinel of src/interpol.c:64-65)
-    constexpr int KR = KMAX > 0 ? KMAX : 1;
-    float rres[KR];           // raw residuals of this lane's picks
-    unsigned cps = 0u;        // their class codes 2*class + phase, four bits each (KMAX <= 8)
+    float* keep_l = &res_keep[KEEP ? wib : 0][0][lane];     // raw residual of this lane's i-th pick at keep_l[32 i]
 
     auto one_pick = [&](int j) -> float {
-        const bool isS = (j - b) >= npk;
+        const int isS = ((j - b) >= npk) ? 1 : 0;
         const float dx = __fsub_rn(p.pk.x[j], ex), dy = __fsub_rn(p.pk.y[j], ey);
         const float dist = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         float tt;
-        if (p.eikonal == 0) {
+        if (RAY) {
             const float r2 = __fadd_rn(__fmul_rn(dist, dist), __fmul_rn(ez, ez));
             tt = (float)(sqrt((double)r2) / (double)(isS ? v0s : v0p));
         } else if (POW2) {
-            // x1 = m1*h, x2 = (m1+1)*h and their difference are exact: the prefactor is 1/(h*h), a power of two
             const int m1 = (int)__fmul_rn(dist, p.rh);
             const bool out = wz.oob || m1 >= p.nxmod - 1;
             oob = oob || out;
-            const float x1 = __fmul_rn((float)m1, p.hgrid), x2 = __fmul_rn((float)(m1 + 1), p.hgrid);
-            const float wa = __fsub_rn(x2, dist), wb = __fsub_rn(dist, x1);
-            const float* row = (isS ? tabSz : tabPz) + (size_t)p.pk.r0[j] * rowsz + (out ? 0 : m1);
+            const float wa = __fsub_rn(__fmul_rn((float)(m1 + 1), p.hgrid), dist), wb = __fsub_rn(dist, __fmul_rn((float)m1, p.hgrid));
+            const float* q = (isS ? tabSz : tabPz) + (p.pk.r0[j] * rowsz + (out ? 0 : m1));
             float t12[2];
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const float* q = row + (size_t)r * rowsz;
+            for (int r = 0; r < 2; r++, q += rowsz) {
                 const float v1 = __ldg(q), v2 = __ldg(q + 1), v3 = __ldg(q + p.xp), v4 = __ldg(q + p.xp + 1);
                 float s4 = __fmul_rn(__fmul_rn(v1, wa), wz.c);
                 s4 = __fadd_rn(s4, __fmul_rn(__fmul_rn(v2, wb), wz.c));
@@ -348,17 +409,17 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, (KMAX > 4 ? 6 : 8)) misfit_
         } else {
             const BilinearX w = bilinear_dist(wz, dist, p.hgrid, p.rh, false, p.nxmod);
             oob = oob || w.oob;
-            const float* row = (isS ? tabSz : tabPz) + (size_t)p.pk.r0[j] * rowsz;
+            const float* row = (isS ? tabSz : tabPz) + p.pk.r0[j] * rowsz;
             const float t1 = w.oob ? 1e30f : bilinear_eval(wz, w, row, p.xp);
             const float t2 = w.oob ? 1e30f : bilinear_eval(wz, w, row + rowsz, p.xp);
             tt = __fadd_rn(__fmul_rn(t1, p.pk.w1[j]), __fmul_rn(t2, p.pk.w2[j]));
         }
         const int st = p.pk.st_id[j];
         float corr = isS ? sres[st] : pres[st];
-        if (ridx >= 0) {   // proposed station-correction perturbation (src/mcmc_eq.c:910-928)
-            const float d1 = isS ? rd[1] : rd[0], d2 = isS ? rd[3] : rd[2];
-            if (p.scor_flag <= 0) corr = (st == ridx) ? __fadd_rn(corr, d1) : __fsub_rn(corr, __fdiv_rn(d1, nsm1));
-            if (p.scor_flag != 0 && st == ridx) corr = __fadd_rn(corr, d2);
+        if (ridx >= 0) {
+            const bool self = st == ridx;
+            if (p.scor_flag <= 0) corr = self ? __fadd_rn(corr, isS ? rd1S : rd1P) : __fsub_rn(corr, isS ? rq1S : rq1P);
+            if (p.scor_flag != 0 && self) corr = __fadd_rn(corr, isS ? rd2S : rd2P);
         }
         if (corr < -1000.f) atomicOr(p.err, kErrStatcor);
         tt = __fadd_rn(tt, corr);
@@ -366,23 +427,12 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, (KMAX > 4 ? 6 : 8)) misfit_
         return __fsub_rn(tt, p.pk.t[j]);
     };
 
-    if (KMAX > 0) {
-#pragma unroll
-        for (int i = 0; i < KR; i++) {
-            const int j = b + lane + 32 * i;
-            rres[i] = 0.f;
-            if (j < end) {
-                rres[i] = one_pick(j);
-                sum += rres[i];
-                cps |= (unsigned)p.pk.cp[j] << (4 * i);
-            }
-        }
-    } else {
-        for (int j = b + lane; j < end; j += 32) {
-            const float diff = one_pick(j);
-            resid[j] = diff;
-            sum += diff;
-        }
+#pragma unroll 2
+    for (int j = b + lane, i = 0; j < end; j += 32, i++) {
+        const float diff = one_pick(j);
+        if (KEEP) keep_l[32 * i] = diff;
+        else resid[j] = diff;
+        sum += diff;
     }
     sum = warp_sum(sum);
     const float mean = sum / (float)(end - b);
@@ -391,23 +441,10 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, (KMAX > 4 ? 6 : 8)) misfit_
     float* acc_l = &class_acc[wib][0][lane];
 #pragma unroll
     for (int k = 0; k < 8; k++) acc_l[k * 32] = 0.f;
-    if (KMAX > 0) {
-#pragma unroll
-        for (int i = 0; i < KR; i++) {
-            const int j = b + lane + 32 * i;
-            if (j < end) {
-                const float d = __fsub_rn(rres[i], mean);
-                if (p.tpred) resid[j] = d;
-                const int cp = (cps >> (4 * i)) & 15;
-                acc_l[cp * 32] += d * d;
-            }
-        }
-    } else {
-        for (int j = b + lane; j < end; j += 32) {
-            const float d = __fsub_rn(resid[j], mean);
-            if (p.tpred) resid[j] = d;
-            acc_l[p.pk.cp[j] * 32] += d * d;
-        }
+    for (int j = b + lane, i = 0; j < end; j += 32, i++) {
+        const float d = __fsub_rn(KEEP ? keep_l[32 * i] : resid[j], mean);
+        if (p.tpred) resid[j] = d;
+        acc_l[p.pk.cp[j] * 32] += d * d;
     }
     float acc[8];
 #pragma unroll
@@ -449,20 +486,31 @@ cudaError_t launch_misfit(Handle* h, const EvalView& v)
     const unsigned grid = (unsigned)((tasks + kMisfitWarps - 1) / kMisfitWarps);
     const int per_lane = (h->pk.max_event_picks + 31) / 32;
     // the per-pick scratch exists when an event is too large for the register path or predictions are wanted
-    if ((per_lane > 8 || h->want_pred) && !h->resid) {
+    if ((per_lane > kMisfitKeep || h->want_pred) && !h->resid) {
         const cudaError_t e = cudaMalloc(&h->resid, (size_t)h->n * h->np * sizeof(float));
         if (e != cudaSuccess) return e;
         p.resid = h->resid;
     }
-#define MISFIT_LAUNCH(K)                                                                               \
+#define MISFIT_LAUNCH(KEEP)                                                                            \
     do {                                                                                               \
-        if (p.h_pow2) misfit_kernel<K, true><<<grid, kMisfitWarps * 32, 0, h->stream>>>(p);            \
-        else misfit_kernel<K, false><<<grid, kMisfitWarps * 32, 0, h->stream>>>(p);                    \
+        if (p.eikonal == 0) misfit_kernel<KEEP, false, true><<<grid, kMisfitWarps * 32, 0, h->stream>>>(p);        \
+        else if (p.h_pow2) misfit_kernel<KEEP, true, false><<<grid, kMisfitWarps * 32, 0, h->stream>>>(p);         \
+        else misfit_kernel<KEEP, false, false><<<grid, kMisfitWarps * 32, 0, h->stream>>>(p);                      \
     } while (0)
-    if (per_lane <= 4) MISFIT_LAUNCH(4);
-    else if (per_lane <= 8) MISFIT_LAUNCH(8);
-    else MISFIT_LAUNCH(0);
+    static int force_scratch = -1;      // MCMCEQ_MISFIT_SCRATCH=1: residuals through the global scratch (the round-1 data flow)
+    if (force_scratch < 0) { const char* e = getenv("MCMCEQ_MISFIT_SCRATCH"); force_scratch = (e && e[0] == '1') ? 1 : 0; }
+    if (force_scratch && !h->resid) {
+        const cudaError_t e = cudaMalloc(&h->resid, (size_t)h->n * h->np * sizeof(float));
+        if (e != cudaSuccess) return e;
+        p.resid = h->resid;
+    }
+    Profile* pr = (Profile*)h->prof;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (pr && pr->enabled) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
+    if (per_lane <= kMisfitKeep && !force_scratch) MISFIT_LAUNCH(true);
+    else MISFIT_LAUNCH(false);
 #undef MISFIT_LAUNCH
+    if (e0) { cudaEventRecord(e1, h->stream); pr->mev.push_back(e0); pr->mev.push_back(e1); }
     count_launch();
     return cudaGetLastError();
 }
