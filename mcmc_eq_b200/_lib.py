@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmcmceq_b200.so")
+# MCMCEQ_LIB: an alternative build of the same library (A/B experiments, tools/ab_build.py); the default is the in-tree build
+LIB_PATH = os.environ.get("MCMCEQ_LIB") or os.path.join(_PKG, "libmcmceq_b200.so")
 _lib = None
 
 fp = C.POINTER(C.c_float)

@@ -64,7 +64,7 @@ def build_emu(force: bool = False) -> str:
     """Host build of the CUDA solver core, used by the CPU tests only."""
     src = os.path.join(ROOT, "tests", "emu", "eik_emu.cpp")
     out = os.path.join(ROOT, "tests", "emu", "libeik_emu.so")
-    deps = [src, os.path.join(CSRC, "eik_core.cuh")]
+    deps = [src, os.path.join(CSRC, "eik_core.cuh"), os.path.join(CSRC, "eik_fast.cuh")]
     if force or not _newer(out, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused-but-set-variable",
                         src, "-o", out], check=True)
