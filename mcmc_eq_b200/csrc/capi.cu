@@ -107,7 +107,7 @@ extern "C" int mq_destroy(mq_handle* hh)
     free_view(&h->cur_view); free_view(&h->prop_view);
     cudaFree(h->evq); cudaFree(h->oq); cudaFree(h->mf_eval); cudaFree(h->resid); cudaFree(h->tpred);
     cudaFree(h->item_chain); cudaFree(h->item_phase); cudaFree(h->n_items); cudaFree(h->slow); cudaFree(h->item_tab);
-    cudaFree(h->solve_status); cudaFree(h->scratch); cudaFree(h->eik_order); cudaFree(h->eik_order_work); cudaFree(h->eik_task_counter); cudaFree(h->eik_tie_scratch);
+    cudaFree(h->solve_status); cudaFree(h->scratch); cudaFree(h->eik_slice_scratch); cudaFree(h->eik_order); cudaFree(h->eik_order_work); cudaFree(h->eik_task_counter); cudaFree(h->eik_tie_scratch);
     if (h->host_flags) cudaFreeHost(h->host_flags);
     if (h->flags_ev) cudaEventDestroy(h->flags_ev);
     for (int i = 0; i < 2; i++)
@@ -230,23 +230,28 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const long need = ((long)2 * n * h->nz + 31) / 32;
-        long warps = std::min<long>(need, (long)sms * 16);
-        // large planes (the 0.1 km fine-grid case: 565 x 2001 nodes = 145 MB per warp): never more than a quarter of the
-        // free device memory; the kernels loop over the tasks with however many warps they are given
+        const bool fine = !eik_fast_supported(h->nxmod, h->nz);
+        long warps = std::min<long>(need, (long)sms * (fine ? 12 : 16));
+        // large planes (the 0.1 km fine-grid case: 565 x 2001 nodes = 145 MB of window + 0.8 MB of slice per warp): never
+        // more than half of the device memory that is still free (the tables are allocated); the kernels loop over the
+        // tasks with however many warps they are given.  MCMCEQ_SCRATCH_FRACTION overrides the fraction.
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t per_warp = eik_scratch_floats_per_warp(h->nxmod, h->nz) * sizeof(float);
-            const long by_mem = (long)((free_b / 4) / per_warp);
+            double frac = fine ? 0.5 : 0.25;
+            if (const char* e = getenv("MCMCEQ_SCRATCH_FRACTION")) { const double f = atof(e); if (f > 0.0 && f < 0.95) frac = f; }
+            const size_t per_warp = (eik_scratch_floats_per_warp(h->nxmod, h->nz) + (fine ? eik_fine_slice_floats_per_warp(h->nxmod, h->nz) : 0)) * sizeof(float);
+            const long by_mem = (long)(((double)free_b * frac) / (double)per_warp);
             warps = std::min<long>(warps, std::max<long>(by_mem, 4));
         }
         warps = (warps + 3) / 4 * 4;
         h->scratch_warps = (int)warps;
         TRY(cudaMalloc(&h->scratch, (size_t)warps * eik_scratch_floats_per_warp(h->nxmod, h->nz) * sizeof(float)));
+        if (fine) TRY(cudaMalloc(&h->eik_slice_scratch, (size_t)warps * eik_fine_slice_floats_per_warp(h->nxmod, h->nz) * sizeof(float)));
     }
     {
         // regrouping of the solves of a table rebuild (MCMCEQ_EIKONAL_ORDER=0 keeps the natural order)
         const char* e = getenv("MCMCEQ_EIKONAL_ORDER");
-        if (!(e && e[0] == '0') && eik_fast_supported(h->nxmod, h->nz)) {
+        if (!(e && e[0] == '0') && h->nz <= 4096) {      // the sort key holds the source depth in 12 bits
             const int max_solves = 2 * n_chains * h->nz;
             h->eik_order_bytes = eik_order_bytes(max_solves);
             TRY(cudaMalloc(&h->eik_order_work, h->eik_order_bytes));
@@ -545,6 +550,7 @@ extern "C" int mq_get_table(mq_handle* hh, int chain, int phase, float* ttt)
     EikBatch b = {};
     b.nxmod = nx; b.nz = nz; b.slow = d_slow; b.n_items = nz; b.src_iz = d_iz; b.n_solves = nz;
     b.full_out = d_out; b.status_min = h->solve_status; b.scratch = h->scratch; b.max_warps = h->scratch_warps;
+    b.slice_scratch = h->eik_slice_scratch;
     MQ_CUDA(eik_launch(b, s));
     std::vector<float> t((size_t)nz * nodes);
     MQ_CUDA(d2h(t.data(), d_out, t.size(), s));

@@ -181,9 +181,11 @@ EIK_HD bool headwave_fires(float c, float cn, float hs2)
 // hint (may be nullptr): in: index of the first local minimum of P if known (>= 0); out: the same for C, found
 // as C is written (valid when the next sweep covers the same [kb, ke]: the march), or -1.
 // Returns true for lanes that must re-do the line on the slow path.
+// kedge (rows of the coarse grid only, else -1): node of the row whose cell on the far side along the row is the masked
+// dummy column (src/time_2d.c:489-496): the row reaches the right edge of the grid, X1 == mx.
 template <bool ROW>
 EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inplace, int kb, int ke, const Med& med,
-                       float c, float c2, float* Wt, long wstride, int* hint)
+                       float c, float c2, float* Wt, long wstride, int* hint, int kedge = -1)
 {
     enum { SEG = 0, WALK = 1, DONE = 2 };
     const bool hw = ROW && (c2 < c);
@@ -216,7 +218,7 @@ EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inpl
             kmin = k;
             pmin = pk;
             float sm;
-            if (ROW) { sp = c; sm = (k == 0) ? kInf : c; }
+            if (ROW) { sp = (k == kedge) ? kInf : c; sm = (k == 0) ? kInf : c; }
             else { sp = med.cell(k); sm = (k == 0) ? kInf : med.cell(k - 1); }
             const float est = pk + eik::fmin_ref(sm, sp);      // 1-D transmission in front of the minimum
             cmin = (est < kInf) ? est : kInf;
@@ -252,7 +254,7 @@ EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inpl
                 if (inplace && seen && eq_tail) slow = true;   // the walk would go on over overwritten values
                 const bool use3 = (d > 0) || (kk != 0);
                 float hs0, hs1;
-                if (ROW) { hs0 = c; hs1 = c; }
+                if (ROW) { hs0 = c; hs1 = (d > 0 && kk == kedge) ? kInf : c; }
                 else { hs0 = s0; hs1 = use3 ? med.cell((d > 0) ? kk : kk - 1) : 0.f; }
                 const float cold = seen ? C[(long)kk * stride] : kInf;
                 const float cv = node_update(cold, pk2, pn, cn, hs0, hs1, use3);
@@ -302,14 +304,18 @@ EIK_HD bool row_is_monotone(bool act, const float* R, int stride, int ke)
     return ok;
 }
 
-EIK_HD bool row_march(bool act, float* R, int stride, int ke, float c, float c2, float* Wt, long wstride, bool* mono)
+// EDGE: some lane's row reaches the right edge of the coarse grid (kedge == its last node, else -1): the cell beyond that
+// node is the masked dummy column, so it has no 1-D transmission towards the future.
+template <bool EDGE>
+EIK_HD bool row_march(bool act, float* R, int stride, int ke, float c, float c2, float* Wt, long wstride, bool* mono, int kedge = -1)
 {
     const bool hw = c2 < c;
     bool slow = false, mn = true;
     float pn = 0.f, cn = 0.f;
     if (act) {
         pn = R[0];
-        const float est = pn + eik::fmin_ref(kInf, c);       // 1-D transmission in front of the minimum (node 0: no cell before it)
+        // 1-D transmission in front of the minimum (node 0: no cell before it; a one-node row at the edge: none after it either)
+        const float est = pn + eik::fmin_ref(kInf, (EDGE && kedge == 0) ? kInf : c);
         cn = (est < kInf) ? est : kInf;
         R[0] = cn;
         if (Wt) Wt[0] = cn;
@@ -317,7 +323,7 @@ EIK_HD bool row_march(bool act, float* R, int stride, int ke, float c, float c2,
     for (int k = 1; EIKF_ANY(act && !slow && k <= ke); k++) {
         if (act && !slow && k <= ke) {
             const float pk = R[(long)k * stride];
-            const float cv = node_update(kInf, pk, pn, cn, c, c, true);
+            const float cv = node_update(kInf, pk, pn, cn, c, (EDGE && k == kedge) ? kInf : c, true);
             if (hw && headwave_fires(cv, cn, c2)) slow = true;
             R[(long)k * stride] = cv;
             if (Wt) Wt[(long)k * wstride] = cv;
@@ -678,22 +684,26 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 bool slow = false, refill = true;
                 if (need) {
                     line = --b.Y0;
-                    // the coarse grid's last column of cells is masked (INF): rows that reach it take the generic sweep;
-                    // the refined grid is not masked (src/time_2d.c:466), its rows are uniform up to the edge
-                    if (b.preset_up || (!FINE && b.X1 >= b.mx)) { slow = true; refill = false; }
+                    if (b.preset_up) { slow = true; refill = false; }
                 }
+                // the coarse grid's last column of cells is masked (INF, src/time_2d.c:489-496): the last node of a row that
+                // reaches it has no cell beyond it; the refined grid is not masked (:466), its rows are uniform up to the edge
+                const bool edge = !FINE && b.X1 >= b.mx;
                 const float c = need ? rowS(line) : 1.f;
                 const float c2 = (need && line - 1 >= 0) ? rowS(line - 1) : kInf;   // far < 0: no head wave
                 const bool fastlane = need && !slow;
                 bool s2;
-                if (D.row_march && row_ready(fastlane, L.ROW, LS, b.X1, mono_top))
-                    s2 = row_march(fastlane, L.ROW, LS, b.X1, c, c2, T + (size_t)line * LS, (long)b.ny * LS, &mono_top);
-                else {
+                if (D.row_march && row_ready(fastlane, L.ROW, LS, b.X1, mono_top)) {
+                    float* wt = T + (size_t)line * LS;
+                    s2 = EIKF_ANY(fastlane && edge)
+                             ? row_march<true>(fastlane, L.ROW, LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_top, edge ? b.X1 : -1)
+                             : row_march<false>(fastlane, L.ROW, LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_top);
+                } else {
 #ifdef EIKF_STATS
                     if (fastlane) g_stats[8]++;
 #endif
                     s2 = fast_sweep<true>(fastlane, L.ROW, L.ROW, LS, true, 0, b.X1, med, c, c2,
-                                          T + (size_t)line * LS, (long)b.ny * LS, nullptr);
+                                          T + (size_t)line * LS, (long)b.ny * LS, nullptr, edge ? b.X1 : -1);
                     mono_top = false;
                 }
                 if (need && (slow || s2)) {
@@ -746,23 +756,24 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 moved = true;
                 int line = 0;
                 bool slow = false;
-                if (need) {
-                    line = ++b.Y1;
-                    if (!FINE && b.X1 >= b.mx) slow = true;
-                }
+                if (need) line = ++b.Y1;
+                const bool edge = !FINE && b.X1 >= b.mx;
                 const float c = need ? rowS(line - 1) : 1.f;
                 const float c2 = need ? rowS(line) : kInf;
                 float* bot = L.ROW + (size_t)(RL - 1) * LS;
                 const bool fastlane = need && !slow;
                 bool s2;
-                if (D.row_march && row_ready(fastlane, bot, -LS, b.X1, mono_bot))
-                    s2 = row_march(fastlane, bot, -LS, b.X1, c, c2, T + (size_t)line * LS, (long)b.ny * LS, &mono_bot);
-                else {
+                if (D.row_march && row_ready(fastlane, bot, -LS, b.X1, mono_bot)) {
+                    float* wt = T + (size_t)line * LS;
+                    s2 = EIKF_ANY(fastlane && edge)
+                             ? row_march<true>(fastlane, bot, -LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_bot, edge ? b.X1 : -1)
+                             : row_march<false>(fastlane, bot, -LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_bot);
+                } else {
 #ifdef EIKF_STATS
                     if (fastlane) g_stats[8]++;
 #endif
                     s2 = fast_sweep<true>(fastlane, bot, bot, -LS, true, 0, b.X1, med, c, c2,
-                                          T + (size_t)line * LS, (long)b.ny * LS, nullptr);
+                                          T + (size_t)line * LS, (long)b.ny * LS, nullptr, edge ? b.X1 : -1);
                     mono_bot = false;
                 }
                 if (need && (slow || s2)) {

@@ -105,13 +105,17 @@ bool eik_fast_supported(int nxmod, int nz)
 }
 
 // One warp per block: a warp owns 32 solves and its slice of shared memory, nothing is shared between warps.
-__global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims D)
+// GLOBAL_SLICE (eik_fine_kernel): planes whose perimeter does not fit shared memory (the 0.1 km fine grid: 2001 depth nodes,
+// 6010 floats per lane) keep the same three arrays in a per-warp slice of GLOBAL memory, lane-interleaved like the
+// shared-memory slice, so that the lock-step sweeps (rows, the march) touch one 128-byte line per access.  Same code,
+// same results; what hides the memory latency is the number of resident warps.
+template <bool GLOBAL_SLICE>
+__device__ __forceinline__ void eik_fast_body(const EikBatch& b, const eikf::Dims& D, float* slice)
 {
-    extern __shared__ float smem[];
     const int lane = threadIdx.x;
     const int nodes = b.nxmod * b.nz;
     eikf::Lane L;
-    eikf::carve_shared(smem + lane, D, &L);
+    eikf::carve_shared(slice + lane, D, &L);
     L.W = b.scratch + (size_t)blockIdx.x * (((size_t)D.wx * D.nz + kFineNodes) * 32) + lane;
     L.WF = L.W + (size_t)D.wx * D.nz * 32;
     const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
@@ -145,6 +149,17 @@ __global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims 
         }
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims D)
+{
+    extern __shared__ float smem[];
+    eik_fast_body<false>(b, D, smem);
+}
+
+__global__ void __launch_bounds__(32, 12) eik_fine_kernel(EikBatch b, eikf::Dims D)
+{
+    eik_fast_body<true>(b, D, b.slice_scratch + (size_t)blockIdx.x * ((size_t)eikf::smem_floats_per_lane(D) * 32));
 }
 
 // ---- regrouping of solves --------------------------------------------------------------------------------------
@@ -530,6 +545,31 @@ const char* eik_kernel_name(int which)
     return (which >= 0 && which < kEikKernels) ? names[which] : "?";
 }
 
+size_t eik_fine_slice_floats_per_warp(int nxmod, int nz)
+{
+    return fast_smem_floats_per_warp(fast_dims(nxmod, nz));
+}
+
+cudaError_t eik_launch_fine(const EikBatch& b, cudaStream_t stream)
+{
+    const int n_solves = b.src_iz ? b.n_solves : b.n_items * b.nz;
+    if (n_solves <= 0) return cudaSuccess;
+    if (!b.slice_scratch) return cudaErrorInvalidValue;
+    const eikf::Dims D = fast_dims(b.nxmod, b.nz);
+    EikBatch bb = b;
+    bb.lanes_per_task = 32;
+    const int n_tasks = (n_solves + 31) / 32;
+    // one warp per CTA; the window (b.scratch) and the slice were sized for max_warps warps
+    const size_t have = (size_t)b.max_warps * eik_scratch_floats_per_warp(b.nxmod, b.nz);
+    long warps = (long)(have / fast_scratch_floats_per_warp(D));
+    if (warps > b.max_warps) warps = b.max_warps;
+    if (warps > n_tasks) warps = n_tasks;
+    if (warps < 1) warps = 1;
+    eik_fine_kernel<<<(unsigned)warps, 32, 0, stream>>>(bb, D);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream, int* which)
 {
     int dummy;
@@ -555,6 +595,7 @@ cudaError_t eik_launch(const EikBatch& b, cudaStream_t stream, int* which)
         }
     }
     if (!force_generic && eik_fast_supported(b.nxmod, b.nz)) { *which = kEikFast; return eik_launch_fast(b, stream); }
+    if (!force_generic && b.slice_scratch && b.nxmod >= 2 && b.nz >= 2) { *which = kEikFine; return eik_launch_fine(b, stream); }
     *which = kEikGeneric;
     return eik_launch_generic(b, stream);
 }

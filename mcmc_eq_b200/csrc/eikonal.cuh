@@ -42,6 +42,9 @@ struct EikBatch {
     // Scratch: per resident warp (nxmod*nz + kFineNodes) * 32 floats.
     float* scratch;
     int max_warps;
+    // Planes that do not fit a shared-memory slice (eik_fine_kernel): eik_fine_slice_floats_per_warp() floats per warp for
+    // max_warps warps, or nullptr (such planes then take the generic kernel).
+    float* slice_scratch;
 };
 
 constexpr int kFineNodes = 22 * 43;   // refined grid of a left-edge source, src/time_2d.c:844-864
@@ -53,6 +56,9 @@ cudaError_t eik_launch_generic(const EikBatch& b, cudaStream_t stream);
 // is smaller (box window + refined grid) so the generic kernel's scratch always suffices.
 bool eik_fast_supported(int nxmod, int nz);
 cudaError_t eik_launch_fast(const EikBatch& b, cudaStream_t stream);
+// The same warp-synchronous solver with its per-lane arrays in global memory, for planes of any size (the fine grid).
+size_t eik_fine_slice_floats_per_warp(int nxmod, int nz);
+cudaError_t eik_launch_fine(const EikBatch& b, cudaStream_t stream);
 // One persistent CTA per SM, 16 warps: box phases on a pool of shared-memory slices, marches on a pool of TMEM sets.
 bool eik_pipe_supported(int nxmod, int nz);
 size_t eik_pipe_tie_floats();

@@ -181,7 +181,7 @@ cudaError_t launch_tables(Handle* h, int max_items)
     b.slow = h->slow; b.n_items = max_items; b.n_items_dev = h->n_items;
     b.row_out = h->item_tab; b.rows = h->d_rows; b.n_rows = h->n_rows; b.xpitch = h->xp;
     b.status_min = h->solve_status;
-    b.scratch = h->scratch; b.max_warps = h->scratch_warps;
+    b.scratch = h->scratch; b.max_warps = h->scratch_warps; b.slice_scratch = h->eik_slice_scratch;
     if (h->eik_order) {
         const cudaError_t e = eik_order_tasks(b, h->eik_order, h->eik_order_work, h->eik_order_bytes, h->stream);
         if (e != cudaSuccess) return e;

@@ -116,6 +116,7 @@ struct Handle {
     int32_t* solve_status; // [1] min over solves
     float* scratch;      // eikonal scratch
     int scratch_warps;
+    float* eik_slice_scratch;    // per-warp global-memory slices of the fine-grid kernel (eikonal.cuh), or nullptr
     int32_t* eik_task_counter;   // work counter and tie scratch of the pipelined eikonal kernel (eikonal.cuh), or nullptr
     float* eik_tie_scratch;
     int32_t* eik_order;  // [round_up(2n*nz, 32)] execution order of the solves of a table rebuild (eikonal.cuh), or nullptr

@@ -26,22 +26,26 @@ EXAMPLE_LIKE = dict(
 )
 
 
+# BASELINE.json configs[4]: 0.1 km grid to 200 km depth, 40 km aperture (eikonal plane 565 x 2001)
+FINE_GRID = dict(h=0.1, nx=400, ny=400, nz=2001, x0=-20.0, y0=-20.0, z0=0.0, sdevxs=0.3, sdevys=0.3, sdevzs=0.5)
+
+
 def config(**override) -> MqConfig:
     d = dict(EXAMPLE_LIKE)
     d.update(override)
     return config_from_dict(d)
 
 
-def geometry(n_events: int, n_stations: int, seed: int = 33, aperture: float = 1.0):
+def geometry(n_events: int, n_stations: int, seed: int = 33, aperture: float = 1.0, elev=(-2.0, 0.0), depth=(0.0, 60.0)):
     """Stations, events, classes, station corrections (before travel times exist)."""
     rng = np.random.default_rng(seed)
     r = 120.0 * aperture * np.sqrt(rng.uniform(0, 1, n_stations))
     th = rng.uniform(0, 2 * np.pi, n_stations)
     # 3 decimals, the precision of the pick-file format
     sx, sy = np.round(r * np.cos(th), 3), np.round(r * np.sin(th), 3)
-    sz = np.round(rng.uniform(-2.0, 0.0, n_stations), 3)
+    sz = np.round(rng.uniform(elev[0], elev[1], n_stations), 3)
     ev = np.stack([rng.uniform(-50, 50, n_events) * aperture, rng.uniform(-50, 50, n_events) * aperture,
-                   rng.uniform(0.0, 60.0, n_events)], axis=1).astype(np.float32)
+                   rng.uniform(depth[0], depth[1], n_events)], axis=1).astype(np.float32)
     pcor = rng.normal(0, 0.3, n_stations); pcor -= pcor.mean()
     scor = rng.normal(0, 0.5, n_stations); scor -= scor.mean()
     cls = rng.integers(0, 4, (n_events, 2, n_stations))
@@ -62,12 +66,16 @@ def picks_from(geo, t=None) -> Picks:
 
 
 def workload(n_events: int = 200, n_stations: int = 50, seed: int = 33, device: int = 0, rms: float = 0.10, predictor=None,
-             **cfg_override):
+             fine: bool = False, **cfg_override):
     """-> (config, picks, truth) with travel times predicted from the truth model + noise.  The prediction comes from the
     GPU library, or from `predictor(cfg, picks, truth_state) -> t_pred[n_picks]` when given (bench.py's reference arm
     passes the CPU oracle there so that nothing of this library runs in that arm)."""
-    cfg = config(**cfg_override)
-    geo = geometry(n_events, n_stations, seed)
+    if fine:      # the fine-grid stress case: stations on the surface of a 40 km wide array, events down to 180 km
+        cfg = config(**dict(FINE_GRID, **cfg_override))
+        geo = geometry(n_events, n_stations, seed, aperture=1.0 / 6.0, elev=(0.0, 0.15), depth=(1.0, 180.0))
+    else:
+        cfg = config(**cfg_override)
+        geo = geometry(n_events, n_stations, seed)
     pk0 = picks_from(geo)
     if predictor is not None:
         tpred = np.asarray(predictor(cfg, pk0, dict(z=TRUTH_Z, vp=TRUTH_VP, vpvs=TRUTH_VPVS, eq=geo["ev"], pres=geo["pcor"],
