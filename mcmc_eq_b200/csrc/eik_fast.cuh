@@ -42,10 +42,14 @@ using eik::kSqrt2;
 constexpr int LS = 32;   // lane stride of the interleaved arrays
 #define EIKF_ANY(p) __any_sync(0xffffffffu, (p))
 #define EIKF_SYNC() __syncwarp()
+#define EIKF_MIN(v) __reduce_min_sync(0xffffffffu, (v))
+#define EIKF_MAX(v) __reduce_max_sync(0xffffffffu, (v))
 #else
 constexpr int LS = 1;
 #define EIKF_ANY(p) (p)
 #define EIKF_SYNC() ((void)0)
+#define EIKF_MIN(v) (v)
+#define EIKF_MAX(v) (v)
 #endif
 
 struct Dims {
@@ -70,6 +74,8 @@ EIK_HD Dims make_dims(int nx, int nz)
 }
 // floats per lane of the three shared arrays: S[-1..nz-1], COL[-1..col_len], ROW[0..row_len-1]
 EIK_HD int smem_floats_per_lane(const Dims& D) { return (D.nz + 1) + (D.col_len + 2) + D.row_len; }
+// the same plus the second column buffer of a slice in global memory (carve_global)
+EIK_HD int gmem_floats_per_lane(const Dims& D) { return smem_floats_per_lane(D) + (D.col_len + 2); }
 
 // One lane's view of the storage.
 struct Lane {
@@ -78,6 +84,7 @@ struct Lane {
     float* ROW;    // shared: top row at [x], bottom row at [row_len-1-x]
     float* W;      // global: coarse box window, node (x,y) at W[(x*nz+y)*LS]
     float* WF;     // global: refined grid, node (x,y) at WF[(x*nyf+y)*LS]
+    float* COL2;   // second column buffer (same shape as COL) when the slice lives in global memory (GM mode), else nullptr
 };
 
 // Medium of the grid being solved, for the fast sweeps: depth cells come from the shared array
@@ -98,6 +105,10 @@ struct Box {
     int X1, Y0, Y1;
     int preset_up;        // row above the box holds pre-set nodes (minimal initialisation)
     int active;
+    // GM mode: the homogeneous seed box [0, sX1] x [sY0, sY1] (slowness shs0) has only its outline and the receiver rows in
+    // the window so far; the interior is filled when a slow path first needs the window (fill_seed_interior)
+    int seed_pending, sX1, sY0, sY1;
+    float shs0;
 };
 
 // Square root of a stencil radicand.  On the device this is the hardware approximation (one MUFU.SQRT, relative
@@ -132,6 +143,17 @@ EIK_HD bool in_zero_lim(float x, float lim)
     return __float_as_uint(x) < __float_as_uint(lim);
 #else
     return x >= 0.f && x < lim;
+#endif
+}
+
+// Write-through of a value to the lane's global window: a streaming store (evict-first), the window is only read back on
+// the rare slow path and by the output copy, and must not push the lanes' live arrays out of L2 (GM mode).
+EIK_HD void wt_store(float* p, float v)
+{
+#ifdef __CUDA_ARCH__
+    __stcs(p, v);
+#else
+    *p = v;
 #endif
 }
 
@@ -306,7 +328,7 @@ EIK_HD bool row_is_monotone(bool act, const float* R, int stride, int ke)
 
 // EDGE: some lane's row reaches the right edge of the coarse grid (kedge == its last node, else -1): the cell beyond that
 // node is the masked dummy column, so it has no 1-D transmission towards the future.
-template <bool EDGE>
+template <bool EDGE, bool PF>
 EIK_HD bool row_march(bool act, float* R, int stride, int ke, float c, float c2, float* Wt, long wstride, bool* mono, int kedge = -1)
 {
     const bool hw = c2 < c;
@@ -320,15 +342,46 @@ EIK_HD bool row_march(bool act, float* R, int stride, int ke, float c, float c2,
         R[0] = cn;
         if (Wt) Wt[0] = cn;
     }
-    for (int k = 1; EIKF_ANY(act && !slow && k <= ke); k++) {
-        if (act && !slow && k <= ke) {
-            const float pk = R[(long)k * stride];
-            const float cv = node_update(kInf, pk, pn, cn, c, (EDGE && k == kedge) ? kInf : c, true);
-            if (hw && headwave_fires(cv, cn, c2)) slow = true;
-            R[(long)k * stride] = cv;
-            if (Wt) Wt[(long)k * wstride] = cv;
-            mn = mn && (cv - cn >= 0.f);
-            pn = pk; cn = cv;
+    if (PF) {
+        // The row lives in global memory: the past values of the NEXT eight nodes are requested before the current eight are
+        // worked on, so a memory latency is paid once per sweep, not once per block.  (The sweep is in place, but a node is
+        // only written after it and everything before it has been read.)
+        constexpr int NB = 16;
+        float nv[NB];
+#pragma unroll
+        for (int u = 0; u < NB; u++) nv[u] = (act && 1 + u <= ke) ? R[(long)(1 + u) * stride] : 0.f;
+        for (int k0 = 1; EIKF_ANY(act && !slow && k0 <= ke); k0 += NB) {
+            float pv[NB];
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                pv[u] = nv[u];
+                nv[u] = (act && k0 + NB + u <= ke) ? R[(long)(k0 + NB + u) * stride] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int k = k0 + u;
+                if (act && !slow && k <= ke) {
+                    const float pk = pv[u];
+                    const float cv = node_update(kInf, pk, pn, cn, c, (EDGE && k == kedge) ? kInf : c, true);
+                    if (hw && headwave_fires(cv, cn, c2)) slow = true;
+                    R[(long)k * stride] = cv;
+                    if (Wt) wt_store(Wt + (long)k * wstride, cv);
+                    mn = mn && (cv - cn >= 0.f);
+                    pn = pk; cn = cv;
+                }
+            }
+        }
+    } else {
+        for (int k = 1; EIKF_ANY(act && !slow && k <= ke); k++) {
+            if (act && !slow && k <= ke) {
+                const float pk = R[(long)k * stride];
+                const float cv = node_update(kInf, pk, pn, cn, c, (EDGE && k == kedge) ? kInf : c, true);
+                if (hw && headwave_fires(cv, cn, c2)) slow = true;
+                R[(long)k * stride] = cv;
+                if (Wt) Wt[(long)k * wstride] = cv;
+                mn = mn && (cv - cn >= 0.f);
+                pn = pk; cn = cv;
+            }
         }
     }
     *mono = mn && !slow;
@@ -449,6 +502,13 @@ EIK_HD void march_sweep(bool act, const float* P, float* C, const float* S, int 
 // follows the reference's order literally.
 // P, C: indices -1 .. ke+1; P's end slots must hold kEdge (set by the caller); S[-1] = S[ke] = INF.
 constexpr float kEdge = 1.0e30f;
+// Sentinel of column node k outside the growing box of a solve with its source at depth node ys (GM mode): above every
+// travel time and strictly increasing away from the source, so that no minimum, no tie and no chain can come from it.
+EIK_HD float gm_sentinel(int k, int ys)
+{
+    const int d = (k > ys) ? k - ys : ys - k;
+    return kEdge * (1.0f + (float)d * (1.0f / 8192.0f));
+}
 
 // ---- the march, both passes in one loop -----------------------------------------------------------------------
 // The two passes never feed each other: a node timed from above cannot have a neighbour above it
@@ -503,11 +563,15 @@ EIK_HD float chain_b_node(ChainB& b, float pprev, float hs1)
     return val;
 }
 
-EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int ke)
+template <bool PF = false>
+EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int ke, float* Wt = nullptr)
 {
     bool tie = false;
-    ChainA a{kEdge, P[0], kInf, kInf};
-    ChainB b{kEdge, P[(long)ke * LS], kInf, kInf};
+    // the cells beyond the two ends of the range: S[-1] = S[ke] = INF for a full column (k = 0 .. my), real cells for a
+    // column of the growing box (the reference's 1-D transmission at a minimum looks at them, src/time_2d.c:995-997)
+    // (the nodes beyond the ends do not exist: a past time above every sentinel keeps the end nodes from being timed from them)
+    ChainA a{4.0f * kEdge, P[0], S[-(long)LS], kInf};
+    ChainB b{4.0f * kEdge, P[(long)ke * LS], S[(long)ke * LS], kInf};
     const float* pa = P + LS;                 // &P[ka + 1]
     const float* sa = S;                      // &S[ka]
     float* ca = C;                            // &C[ka]
@@ -525,15 +589,80 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
         *cb = b_val;
         pa += LS; sa += LS; ca += LS; pb -= LS; sb -= LS; cb -= LS;
     };
+    // Columns in global memory (PF): four nodes of each chain per block, the operands of the NEXT block requested before
+    // the current one is worked on.  In the second half a chain only reads back what the OTHER chain wrote in the first
+    // half, so reading ahead of this half's stores is safe; every node gets its final value exactly once in the second
+    // half, which is where the write-through to the window column Wt (element stride LS, or nullptr) happens.
+    struct Blk { float pa[4], sa[4], pb[4], sb[4], ca[4], cb[4]; };
+    auto load4 = [&](Blk& q, int off, bool merge) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            q.pa[u] = pa[(long)(off + u) * LS]; q.sa[u] = sa[(long)(off + u) * LS];
+            q.pb[u] = pb[-(long)(off + u) * LS]; q.sb[u] = sb[-(long)(off + u) * LS];
+            if (merge) { q.ca[u] = ca[(long)(off + u) * LS]; q.cb[u] = cb[-(long)(off + u) * LS]; }
+        }
+    };
+    auto compute4 = [&](const Blk& q, bool merge) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float a_val = chain_a_node(a, q.pa[u], q.sa[u], tie);
+            float b_val = chain_b_node(b, q.pb[u], q.sb[u]);
+            if (merge) {
+                a_val = fminf(a_val, q.ca[u]);
+                b_val = fminf(b_val, q.cb[u]);
+                if (Wt) { wt_store(Wt + (ca - C) + (long)u * LS, a_val); wt_store(Wt + (cb - C) - (long)u * LS, b_val); }
+            }
+            ca[(long)u * LS] = a_val;
+            cb[-(long)u * LS] = b_val;
+        }
+        pa += 4 * LS; sa += 4 * LS; ca += 4 * LS; pb -= 4 * LS; sb -= 4 * LS; cb -= 4 * LS;
+    };
+    auto run_blocks = [&](int n_blocks, bool merge) {      // n_blocks blocks of four nodes per chain
+        if (n_blocks <= 0) return;
+        Blk cur, nxt, nn;              // two blocks in flight behind the one being worked on
+        load4(cur, 0, merge);
+        if (n_blocks > 1) load4(nxt, 4, merge);
+        for (int blk = 0; blk < n_blocks; blk++) {
+            if (blk + 2 < n_blocks) load4(nn, 8, merge);
+            compute4(cur, merge);
+            cur = nxt;
+            nxt = nn;
+        }
+    };
     struct No { enum { value = 0 }; };
     struct Yes { enum { value = 1 }; };
 
     const int n1 = (ke + 1) >> 1;            // iterations with ka < kb: nobody has been at either node
+    if (PF) {
+        auto step_wt = [&]() {     // one node of each chain in the second half, with write-through
+            float a_val = fminf(chain_a_node(a, *pa, *sa, tie), *ca);
+            *ca = a_val;
+            if (Wt) wt_store(Wt + (ca - C), a_val);
+            float b_val = fminf(chain_b_node(b, *pb, *sb), *cb);
+            *cb = b_val;
+            if (Wt) wt_store(Wt + (cb - C), b_val);
+            pa += LS; sa += LS; ca += LS; pb -= LS; sb -= LS; cb -= LS;
+        };
+        int i = 0;
+        run_blocks(n1 / 4, false);
+        i = (n1 / 4) * 4;
+        for (; i < n1; i++) step(No());
+        if (!(ke & 1)) {   // odd node count: both chains meet on the middle node, the second to arrive merges with the first
+            C[(long)(ke >> 1) * LS] = kInf;
+            step_wt();
+            i++;
+        }
+        const int nb2 = (ke + 1 - i) / 4;
+        run_blocks(nb2, true);
+        i += 4 * nb2;
+        for (; i <= ke; i++) step_wt();
+    } else {
 #pragma unroll 2
-    for (int i = 0; i < n1; i++) step(No());
-    if (!(ke & 1)) C[(long)(ke >> 1) * LS] = kInf;   // odd node count: both chains meet on the middle node
+        for (int i = 0; i < n1; i++) step(No());
+        if (!(ke & 1)) C[(long)(ke >> 1) * LS] = kInf;   // odd node count: both chains meet on the middle node
 #pragma unroll 2
-    for (int i = n1; i <= ke; i++) step(Yes());
+        for (int i = n1; i <= ke; i++) step(Yes());
+    }
     return act && tie;
 }
 
@@ -553,15 +682,16 @@ EIK_HD void copy_strided(float* dst, long ds, const float* src, long ss, int n)
     for (; i < n; i++) dst[(long)i * ds] = src[(long)i * ss];
 }
 
+// col: the buffer that holds the lane's right column (L.COL, or whichever of COL / COL2 is current in GM mode)
 template <class G>
-EIK_HD void load_perimeter(const G& g, const Lane& L, int row_len)
+EIK_HD void load_perimeter(const G& g, const Lane& L, int row_len, float* col)
 {
     // a row is only kept while the box can still grow on that side; the two rows share one buffer
     // (top from the front, bottom from the back) whose length covers them exactly under that rule
     const long xs = (long)g.ny * g.ts;   // node (x,y) of the window lives at t[(x*ny + y)*ts]
     if (g.Y0 > 0) copy_strided(L.ROW, LS, &g.T(0, g.Y0), xs, g.X1 + 1);
     if (g.Y1 < g.my) copy_strided(L.ROW + (size_t)(row_len - 1) * LS, -LS, &g.T(0, g.Y1), xs, g.X1 + 1);
-    copy_strided(L.COL + (size_t)g.Y0 * LS, LS, &g.T(g.X1, g.Y0), g.ts, g.Y1 - g.Y0 + 1);
+    copy_strided(col + (size_t)g.Y0 * LS, LS, &g.T(g.X1, g.Y0), g.ts, g.Y1 - g.Y0 + 1);
 }
 
 template <class Medium>
@@ -576,9 +706,14 @@ EIK_HD eik::Grid<Medium> make_grid(float* t, const Box& b, const Medium& m)
 // Slow path of one line: the generic sweep (with head waves and reverse propagation) on the global
 // copy, then the perimeter is re-read.  `refill`: the fast sweep already wrote part of the line.
 template <int AXIS, class Medium>
-EIK_HD int slow_line(float* t, const Box& b, const Medium& m, const Lane& L, int row_len, int line, int future,
-                     int kb, int ke, bool refill)
+EIK_HD int slow_line(float* t, Box& b, const Medium& m, const Lane& L, int row_len, int line, int future,
+                     int kb, int ke, bool refill, float* col)
 {
+    if (b.seed_pending) {   // the generic sweep may propagate back into the seed box: its interior has to be there
+        for (int x = 0; x <= b.sX1; x++)
+            for (int y = b.sY0; y <= b.sY1; y++) t[((size_t)x * b.ny + y) * LS] = eik::box_time(b.shs0, x, y - b.ys);
+        b.seed_pending = 0;
+    }
     eik::Grid<Medium> g = make_grid(t, b, m);
 #ifdef EIKF_STATS
     g_stats[5]++; g_stats[6] += (ke - kb + 1); if (!refill) g_stats[7]++;
@@ -586,7 +721,7 @@ EIK_HD int slow_line(float* t, const Box& b, const Medium& m, const Lane& L, int
     if (refill)
         for (int k = kb; k <= ke; k++) eik::node<AXIS>(g, line, k) = kInf;
     eik::sweep_line<AXIS>(g, line, future, kb, ke);
-    load_perimeter(g, L, row_len);
+    load_perimeter(g, L, row_len, col);
     return g.status;
 }
 
@@ -609,7 +744,10 @@ EIK_HD bool row_ready(bool act, const float* R, int stride, int ke, bool known)
 // ---- expanding box + march on one grid, all lanes of the warp together --------------------------------
 // FINE selects the medium type of the slow path.  out/rows: receiver-row output of the coarse grid
 // (nullptr on the refined grid); out[r*out_rstride + x] receives t[x][rows[r]].
-template <bool FINE>
+// GM: the lane's arrays live in global memory (eik_fine_kernel): sweeps that run in lock-step read ahead, and a column of
+// the growing box is swept by the two-chain loop of the march (ping-pong between COL and COL2) whenever the lanes agree on
+// its range, instead of the per-lane in-place walk whose every step waits for a global load.
+template <bool FINE, bool GM>
 // hand_col/hand_x1 (coarse grid only, may be nullptr): split mode.  A lane whose box spans the whole depth range
 // writes its right column (hand_col[k*32], k = 0..my) and X1 there and stops; a separate kernel marches on from it.
 EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMedium& cm, int j0, int hy, float* out,
@@ -625,9 +763,18 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
     const int wx = FINE ? b.nx : D.wx;
     bool boxphase = b.active && (b.Y0 > 0 || b.Y1 < b.my);
     float* col = L.COL;      // the lane's current right column
-    float* spare = L.ROW + LS;   // second column buffer (indices -1..ny), valid once the rows are no longer needed
+    // second column buffer (indices -1..ny): the idle row buffer once the rows are no longer needed, or COL2 (GM)
+    float* spare = GM ? L.COL2 : L.ROW + LS;
     int hint = -1;           // first local minimum of the current column (known on the march)
     bool mono_top = false, mono_bot = false;   // the top / bottom row is known not to decrease away from the axis
+    if (GM && !FINE && b.active) {
+        // both column buffers start as sentinels (see the column sweep below); the right column of the seed box is already
+        // in COL (load_perimeter)
+        for (int k = -1; k <= b.ny; k++) {
+            if (k < b.Y0 || k > b.Y1) col[(long)k * LS] = gm_sentinel(k, b.ys);
+            spare[(long)k * LS] = gm_sentinel(k, b.ys);
+        }
+    }
     if (xbox_end) *xbox_end = boxphase ? -1 : b.X1;
     // cell slowness of a row strip, with the masked dummy row of the coarse grid
     auto rowS = [&](int cy) -> float { return (!FINE && cy >= b.my) ? kInf : med.cell(cy); };
@@ -654,7 +801,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 const bool need = b.active && b.X1 < b.mx;
                 int line = 0;
                 if (need) line = ++b.X1;
-                const bool tie = march_sweep3(need, col, spare, L.S, b.my);
+                const bool tie = march_sweep3<GM>(need, col, spare, L.S, b.my);
                 if (EIKF_ANY(tie)) {   // an exact tie in the past column: follow the reference's order literally
                     if (tie) { col[-(long)LS] = kStop; col[(size_t)b.ny * LS] = kStop; }
                     int nohint = -1;
@@ -696,8 +843,8 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 if (D.row_march && row_ready(fastlane, L.ROW, LS, b.X1, mono_top)) {
                     float* wt = T + (size_t)line * LS;
                     s2 = EIKF_ANY(fastlane && edge)
-                             ? row_march<true>(fastlane, L.ROW, LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_top, edge ? b.X1 : -1)
-                             : row_march<false>(fastlane, L.ROW, LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_top);
+                             ? row_march<true, GM>(fastlane, L.ROW, LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_top, edge ? b.X1 : -1)
+                             : row_march<false, GM>(fastlane, L.ROW, LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_top);
                 } else {
 #ifdef EIKF_STATS
                     if (fastlane) g_stats[8]++;
@@ -707,8 +854,8 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                     mono_top = false;
                 }
                 if (need && (slow || s2)) {
-                    const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, -1, 0, b.X1, refill)
-                                        : slow_line<1>(T, b, cm, L, RL, line, -1, 0, b.X1, refill);
+                    const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, -1, 0, b.X1, refill, col)
+                                        : slow_line<1>(T, b, cm, L, RL, line, -1, 0, b.X1, refill, col);
                     if (rc != eik::kOk) status = rc;
                     b.preset_up = 0;
                     mono_top = false;
@@ -723,18 +870,40 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 moved = true;
                 int line = 0;
                 if (need) line = ++b.X1;
-                // While the box is growing the column is swept in place (the row buffer is busy and the window
-                // is there to fall back on); on the march it ping-pongs between the column and the idle row buffer.
-                const bool inplace = boxphase;
-                float* dst = inplace ? col : spare;
                 const bool wt = need && (FINE || boxphase) && line < wx;
-                const bool s2 = fast_sweep<false>(need, col, dst, LS, inplace, b.Y0, b.Y1, med, 0.f, 0.f,
-                                                  wt ? T + (size_t)line * b.ny * LS : nullptr, LS, inplace ? nullptr : &hint);
-                if (need && !inplace) { spare = col; col = dst; }
-                if (need && s2) {   // an exact tie on an in-place column: re-done on the window
-                    const int rc = FINE ? slow_line<0>(T, b, fm, L, RL, line, 1, b.Y0, b.Y1, true)
-                                        : slow_line<0>(T, b, cm, L, RL, line, 1, b.Y0, b.Y1, true);
-                    if (rc != eik::kOk) status = rc;
+                bool lockstep = false;
+                if (GM && !FINE) {
+                    // The two-chain loop of the march over the union of the lanes' ranges.  Outside its own range a lane's
+                    // column buffers hold sentinels that grow away from the source depth (gm_sentinel), so its chains start
+                    // and end at its own Y0 and Y1 exactly as they do at the ends of a full column.
+                    const int kb = EIKF_MIN(need ? b.Y0 : 0x7fffffff), ke = EIKF_MAX(need ? b.Y1 : -1);
+                    lockstep = true;
+                    // (a lane writes through over the whole union range: window nodes outside its own box are untimed and
+                    //  are written again when a sweep of its own times them)
+                    const bool tie = march_sweep3<true>(need, col + (long)kb * LS, spare + (long)kb * LS, L.S + (long)kb * LS, ke - kb,
+                                                        wt ? T + ((size_t)line * b.ny + kb) * LS : nullptr);
+                    if (need) {   // what the sweep left outside this lane's range is not a column value: sentinels again
+                        for (int k = kb; k < b.Y0; k++) spare[(long)k * LS] = gm_sentinel(k, b.ys);
+                        for (int k = b.Y1 + 1; k <= ke; k++) spare[(long)k * LS] = gm_sentinel(k, b.ys);
+                    }
+                    if (EIKF_ANY(tie))   // an exact tie in the past column: the literal walk, ping-pong discipline
+                        fast_sweep<false>(tie, col, spare, LS, false, b.Y0, b.Y1, med, 0.f, 0.f,
+                                          (tie && wt) ? T + (size_t)line * b.ny * LS : nullptr, LS, nullptr);
+                    if (need) { float* tmp = col; col = spare; spare = tmp; }
+                }
+                if (!lockstep) {
+                    // While the box is growing the column is swept in place (the row buffer is busy and the window
+                    // is there to fall back on); on the march it ping-pongs between the column and the idle row buffer.
+                    const bool inplace = boxphase;
+                    float* dst = inplace ? col : spare;
+                    const bool s2 = fast_sweep<false>(need, col, dst, LS, inplace, b.Y0, b.Y1, med, 0.f, 0.f,
+                                                      wt ? T + (size_t)line * b.ny * LS : nullptr, LS, inplace ? nullptr : &hint);
+                    if (need && !inplace) { spare = col; col = dst; }
+                    if (need && s2) {   // an exact tie on an in-place column: re-done on the window
+                        const int rc = FINE ? slow_line<0>(T, b, fm, L, RL, line, 1, b.Y0, b.Y1, true, col)
+                                            : slow_line<0>(T, b, cm, L, RL, line, 1, b.Y0, b.Y1, true, col);
+                        if (rc != eik::kOk) status = rc;
+                    }
                 }
                 if (need) {
                     if (boxphase) {
@@ -766,8 +935,8 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 if (D.row_march && row_ready(fastlane, bot, -LS, b.X1, mono_bot)) {
                     float* wt = T + (size_t)line * LS;
                     s2 = EIKF_ANY(fastlane && edge)
-                             ? row_march<true>(fastlane, bot, -LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_bot, edge ? b.X1 : -1)
-                             : row_march<false>(fastlane, bot, -LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_bot);
+                             ? row_march<true, GM>(fastlane, bot, -LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_bot, edge ? b.X1 : -1)
+                             : row_march<false, GM>(fastlane, bot, -LS, b.X1, c, c2, wt, (long)b.ny * LS, &mono_bot);
                 } else {
 #ifdef EIKF_STATS
                     if (fastlane) g_stats[8]++;
@@ -777,8 +946,8 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                     mono_bot = false;
                 }
                 if (need && (slow || s2)) {
-                    const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, 1, 0, b.X1, !slow)
-                                        : slow_line<1>(T, b, cm, L, RL, line, 1, 0, b.X1, !slow);
+                    const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, 1, 0, b.X1, !slow, col)
+                                        : slow_line<1>(T, b, cm, L, RL, line, 1, 0, b.X1, !slow, col);
                     if (rc != eik::kOk) status = rc;
                     mono_bot = false;
                 }
@@ -810,6 +979,7 @@ struct LaneTask {
     int* hand_x1;        // ... and the column index it belongs to (-1: nothing left to march); nullptr = fused mode
 };
 
+template <bool GM = false>
 EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int* rows, int n_rows)
 {
     const int nx = D.nx, nz = D.nz, mx = nx - 1, my = nz - 1;
@@ -823,6 +993,7 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     const eik::CoarseMedium cm{L.S, LS, mx, my};
     Box bc;   // coarse box
     bc.nx = nx; bc.ny = nz; bc.mx = mx; bc.my = my; bc.ys = t.iz; bc.X1 = 0; bc.Y0 = 0; bc.Y1 = 0; bc.preset_up = 0; bc.active = 0;
+    bc.seed_pending = 0; bc.sX1 = 0; bc.sY0 = 0; bc.sY1 = 0; bc.shs0 = 0.f;
     Box bf = bc;   // refined box
     int j0 = 0, hy = 0;
     bool whole = false;
@@ -834,8 +1005,18 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
         hs0 = eik::source_slowness(g);
         whole = (kind == eik::kSeedBox && g.X1 == mx && g.Y0 == 0 && g.Y1 == my);
         if (!whole) {
-            const int wn = D.wx * nz;
-            for (int i = 0; i < wn; i++) L.W[(size_t)i * LS] = kInf;
+            if (GM) {
+                // Only what can be read before a sweep writes it has to start as INF: the nodes round the source that the
+                // minimal initialisation and the copy-back of the refined grid leave untimed.  Everything else in the window
+                // is written through when it is timed (a window of the fine grid is 4.5 MB per lane).
+                const int xc = (D.wx - 1 < kInitMin + 2) ? D.wx - 1 : kInitMin + 2;
+                const int ylo = (t.iz - kInitMin - 2 > 0) ? t.iz - kInitMin - 2 : 0, yhi = (t.iz + kInitMin + 2 < my) ? t.iz + kInitMin + 2 : my;
+                for (int x = 0; x <= xc; x++)
+                    for (int y = ylo; y <= yhi; y++) L.W[((size_t)x * nz + y) * LS] = kInf;
+            } else {
+                const int wn = D.wx * nz;
+                for (int i = 0; i < wn; i++) L.W[(size_t)i * LS] = kInf;
+            }
             bc.active = 1;
         }
         if (kind == eik::kSeedRefine) {
@@ -852,16 +1033,28 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
             bf.X1 = f.X1; bf.Y0 = f.Y0; bf.Y1 = f.Y1;
             bf.preset_up = (kf == eik::kSeedNearest && ysf > 0 && ysf < bf.my) ? 1 : 0;
             bf.active = 1;
-            load_perimeter(f, L, D.row_len);
+            load_perimeter(f, L, D.row_len, L.COL);
         } else if (!whole) {
-            eik::seed_fill(g, kind);
+            if (GM && kind == eik::kSeedBox && !t.full) {
+                // the outline of the homogeneous box (what the sweeps start from) and its receiver rows (what is output);
+                // the interior follows if a slow path ever looks at it (slow_line)
+                for (int y = g.Y0; y <= g.Y1; y++) g.T(g.X1, y) = eik::box_time(hs0, g.X1, y - t.iz);
+                for (int x = 0; x <= g.X1; x++) { g.T(x, g.Y0) = eik::box_time(hs0, x, g.Y0 - t.iz); g.T(x, g.Y1) = eik::box_time(hs0, x, g.Y1 - t.iz); }
+                if (t.out)
+                    for (int r = 0; r < n_rows; r++)
+                        if (rows[r] > g.Y0 && rows[r] < g.Y1)
+                            for (int x = 0; x <= g.X1; x++) g.T(x, rows[r]) = eik::box_time(hs0, x, rows[r] - t.iz);
+                bc.seed_pending = 1; bc.sX1 = g.X1; bc.sY0 = g.Y0; bc.sY1 = g.Y1; bc.shs0 = hs0;
+            } else {
+                eik::seed_fill(g, kind);
+            }
             bc.preset_up = (kind == eik::kSeedNearest && t.iz > 0 && t.iz < my) ? 1 : 0;
         }
     }
     EIKF_SYNC();
     // ---- refined grids of the lanes that need one
     if (EIKF_ANY(bf.active)) {
-        const int rc = run_grid<true>(bf, L, D, cm, j0, hy, nullptr, 0, nullptr, 0, nullptr, nullptr);
+        const int rc = run_grid<true, GM>(bf, L, D, cm, j0, hy, nullptr, 0, nullptr, 0, nullptr, nullptr);
         if (rc != eik::kOk) status = rc;
         if (bf.active) {
             // every second fine node is a coarse node (src/time_2d.c:887-890); the fine field is complete in WF
@@ -875,14 +1068,14 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     }
     if (bc.active) {
         eik::Grid<eik::CoarseMedium> g = make_grid(L.W, bc, cm);
-        load_perimeter(g, L, D.row_len);
+        load_perimeter(g, L, D.row_len, L.COL);
     }
     EIKF_SYNC();
     // ---- coarse grids
     int xbox_end = -1;
     {
         if (t.hand_x1) *t.hand_x1 = -1;
-        const int rc = run_grid<false>(bc, L, D, cm, 0, 0, t.out, t.out_rstride, rows, n_rows, t.full, &xbox_end, t.hand_col,
+        const int rc = run_grid<false, GM>(bc, L, D, cm, 0, 0, t.out, t.out_rstride, rows, n_rows, t.full, &xbox_end, t.hand_col,
                                        t.hand_x1);
         if (rc != eik::kOk) status = rc;
     }
@@ -914,6 +1107,13 @@ EIK_HD void carve_shared(float* base, const Dims& D, Lane* L)
     L->S = base + (size_t)1 * LS;
     L->COL = L->S + (size_t)D.nz * LS + (size_t)1 * LS;
     L->ROW = L->COL + (size_t)(D.col_len + 1) * LS;
+    L->COL2 = nullptr;
+}
+// the same for a slice in global memory, with the second column buffer behind the rows
+EIK_HD void carve_global(float* base, const Dims& D, Lane* L)
+{
+    carve_shared(base, D, L);
+    L->COL2 = L->ROW + (size_t)D.row_len * LS + (size_t)1 * LS;
 }
 
 }  // namespace eikf

@@ -115,7 +115,8 @@ __device__ __forceinline__ void eik_fast_body(const EikBatch& b, const eikf::Dim
     const int lane = threadIdx.x;
     const int nodes = b.nxmod * b.nz;
     eikf::Lane L;
-    eikf::carve_shared(slice + lane, D, &L);
+    if (GLOBAL_SLICE) eikf::carve_global(slice + lane, D, &L);
+    else eikf::carve_shared(slice + lane, D, &L);
     L.W = b.scratch + (size_t)blockIdx.x * (((size_t)D.wx * D.nz + kFineNodes) * 32) + lane;
     L.WF = L.W + (size_t)D.wx * D.nz * 32;
     const int n_items = b.n_items_dev ? *b.n_items_dev : b.n_items;
@@ -142,7 +143,7 @@ __device__ __forceinline__ void eik_fast_body(const EikBatch& b, const eikf::Dim
             }
             if (b.full_out) t.full = b.full_out + (size_t)g * nodes;
         }
-        const int rc = eikf::solve_warp(D, L, t, b.rows, b.n_rows);
+        const int rc = eikf::solve_warp<GLOBAL_SLICE>(D, L, t, b.rows, b.n_rows);
         if (t.valid) {
             if (b.status) b.status[g] = rc;
             if (b.status_min && rc < 0) atomicMin(b.status_min, rc);
@@ -157,9 +158,9 @@ __global__ void __launch_bounds__(32, 9) eik_fast_kernel(EikBatch b, eikf::Dims 
     eik_fast_body<false>(b, D, smem);
 }
 
-__global__ void __launch_bounds__(32, 12) eik_fine_kernel(EikBatch b, eikf::Dims D)
+__global__ void __launch_bounds__(32, 8) eik_fine_kernel(EikBatch b, eikf::Dims D)
 {
-    eik_fast_body<true>(b, D, b.slice_scratch + (size_t)blockIdx.x * ((size_t)eikf::smem_floats_per_lane(D) * 32));
+    eik_fast_body<true>(b, D, b.slice_scratch + (size_t)blockIdx.x * ((size_t)eikf::gmem_floats_per_lane(D) * 32));
 }
 
 // ---- regrouping of solves --------------------------------------------------------------------------------------
@@ -547,7 +548,7 @@ const char* eik_kernel_name(int which)
 
 size_t eik_fine_slice_floats_per_warp(int nxmod, int nz)
 {
-    return fast_smem_floats_per_warp(fast_dims(nxmod, nz));
+    return (size_t)eikf::gmem_floats_per_lane(fast_dims(nxmod, nz)) * 32;
 }
 
 cudaError_t eik_launch_fine(const EikBatch& b, cudaStream_t stream)

@@ -18,16 +18,21 @@ extern "C" int emu_time_2d(const float* s, int nx, int ny, int iz, float* t, int
 
 // ---- host build of the warp-synchronous solver (csrc/eik_fast.cuh) with a 1-lane warp ----------------
 #include "../../mcmc_eq_b200/csrc/eik_fast.cuh"
+// gm != 0: the variant of the solver for slices in global memory (eik_fine_kernel): read-ahead row sweeps, columns of the
+// growing box by the two-chain loop
+static int g_gm = 0;
+extern "C" void emu_set_gm(int on) { g_gm = on; }
 extern "C" int emu_fast_time_2d(const float* s, int nx, int ny, int iz, float* t, const int* rows, int n_rows, float* rows_out)
 {
     const eikf::Dims D = eikf::make_dims(nx, ny);
-    std::vector<float> SM(eikf::smem_floats_per_lane(D)), W((size_t)D.wx * ny), WF(22 * 43);
+    std::vector<float> SM(eikf::gmem_floats_per_lane(D)), W((size_t)D.wx * ny), WF(22 * 43);
     eikf::Lane L;
-    eikf::carve_shared(SM.data(), D, &L);
+    if (g_gm) eikf::carve_global(SM.data(), D, &L);
+    else eikf::carve_shared(SM.data(), D, &L);
     L.W = W.data(); L.WF = WF.data();
     eikf::LaneTask task;
     task.valid = true; task.iz = iz; task.slow = s; task.out = rows_out; task.out_rstride = nx; task.full = t; task.hand_col = nullptr; task.hand_x1 = nullptr;
-    return eikf::solve_warp(D, L, task, rows, n_rows);
+    return g_gm ? eikf::solve_warp<true>(D, L, task, rows, n_rows) : eikf::solve_warp<false>(D, L, task, rows, n_rows);
 }
 #ifdef EIKF_STATS
 extern "C" void emu_stats(long* out) { for (int i = 0; i < 12; i++) out[i] = eikf::g_stats[i]; }

@@ -17,6 +17,7 @@ def emu():
     L = C.CDLL(build.build_emu())
     L.emu_time_2d.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, C.POINTER(C.c_int)]
     L.emu_fast_time_2d.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp, C.POINTER(C.c_int), C.c_int, fp]
+    L.emu_set_gm.argtypes = [C.c_int]
     return L
 
 
@@ -100,3 +101,38 @@ def test_fast_path_is_bit_identical_to_generic_core(emu, seed, grid):
             assert rc1 == rc2 == 0, (nx, nz, iz, rc1, rc2)
             assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), (nx, nz, kind, iz)
             assert np.array_equal(ro, t1[:, rows].T)
+
+
+@pytest.mark.parametrize("seed,shape", [(21, None), (22, (40, 260)), (23, (12, 90)), (24, (282, 62))])
+def test_global_memory_variant_is_bit_identical(emu, seed, shape):
+    """The solver as eik_fine_kernel instantiates it (slices in global memory: read-ahead row sweeps, columns of the growing
+    box swept by the two-chain loop with the real cells beyond the ends of the range, rows that run along the masked right
+    edge) against the generic core: identical bits for every source depth, on planes that are taller than wide (the box
+    reaches the right edge long before the top and the bottom), with head waves, low-velocity zones and random models."""
+    rng = np.random.default_rng(seed)
+    for trial in range(8 if shape is None else 4):
+        if shape is None:
+            nx, nz = int(rng.integers(2, 120)), int(rng.integers(2, 150))
+        else:
+            nx, nz = shape
+        h, z0 = 1.0, 0.0
+        kind = ["posterior", "contrast", "lvz", "gradient"][trial % 4]
+        z, vp, vpvs = util.voronoi_model(rng, int(rng.integers(1, 21)), z0, z0 + (nz - 1) * h, kind)
+        s = util.rasterise_np(z, vp, vpvs, h, z0, nz, 1 + trial % 2)
+        rows = sorted({0, min(1, nz - 1), nz - 1})
+        step = 1 if nz <= 100 else 7
+        for iz in list(range(0, nz, step)) + [nz - 1]:
+            t1, rc1, _ = _run(emu, s, nx, iz)
+            emu.emu_set_gm(1)
+            t2, ro, rc2 = _run_fast(emu, s, nx, iz, rows)
+            emu.emu_set_gm(0)
+            assert rc1 == rc2 == 0, (nx, nz, iz, rc1, rc2)
+            assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32)), (nx, nz, kind, iz, float(np.abs(t1 - t2).max()))
+            assert np.array_equal(ro, t1[:, rows].T)
+            # receiver rows only (the table build): the homogeneous seed box is filled lazily, outline and receiver rows first
+            emu.emu_set_gm(1)
+            ro2 = np.zeros((len(rows), nx), np.float32)
+            rc3 = emu.emu_fast_time_2d(ptr(util.f32(s)), nx, nz, iz, None, np.ascontiguousarray(rows, np.int32).ctypes.data_as(C.POINTER(C.c_int)),
+                                       len(rows), ptr(ro2))
+            emu.emu_set_gm(0)
+            assert rc3 == 0 and np.array_equal(ro2, t1[:, rows].T), (nx, nz, kind, iz)
