@@ -233,7 +233,8 @@ typedef struct mq_record {
     const float *eq, *origin;          /* [n_events*3], [n_events] */
     const float *pres, *sres;          /* [n_stations]    */
 } mq_record;
-/* Called once per record; pointers are valid during the call only.  Return non-zero to stop. */
+/* Called once per record; pointers are valid during the call only.  Return non-zero to stop: records not yet delivered stay
+ * in their batch (a further mq_batch_deliver call continues with them; the synchronous mq_drain discards them). */
 typedef int (*mq_record_fn)(void* user, const mq_record* rec);
 
 /* Decimated records wait in a device-side ring of `slots` records per chain (default 4, 1..64; MCMCEQ_RING_SLOTS

@@ -233,11 +233,11 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
         const bool fine = !eik_fast_supported(h->nxmod, h->nz);
         long warps = std::min<long>(need, (long)sms * (fine ? 12 : 16));
         // large planes (the 0.1 km fine-grid case: 565 x 2001 nodes = 145 MB of window + 0.8 MB of slice per warp): never
-        // more than half of the device memory that is still free (the tables are allocated); the kernels loop over the
+        // more than 70 % of the device memory that is still free (the tables are allocated); the kernels loop over the
         // tasks with however many warps they are given.  MCMCEQ_SCRATCH_FRACTION overrides the fraction.
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            double frac = fine ? 0.5 : 0.25;
+            double frac = fine ? 0.7 : 0.25;
             if (const char* e = getenv("MCMCEQ_SCRATCH_FRACTION")) { const double f = atof(e); if (f > 0.0 && f < 0.95) frac = f; }
             const size_t per_warp = (eik_scratch_floats_per_warp(h->nxmod, h->nz) + (fine ? eik_fine_slice_floats_per_warp(h->nxmod, h->nz) : 0)) * sizeof(float);
             const long by_mem = (long)(((double)free_b * frac) / (double)per_warp);
@@ -313,14 +313,22 @@ extern "C" int mq_get_models(mq_handle* hh, mq_models* m)
     MQ_CUDA(d2h(dim2.data(), h->dim, 2 * n, s));
     MQ_CUDA(cudaStreamSynchronize(s));
     const int w = std::min(m->max_dim, h->md);
+    // both buffers of the double-buffered arrays in one copy each, the current one of every chain picked on the host
+    // (four transfers whatever the number of chains)
+    std::vector<float> z2(2 * n * h->md), vp2(2 * n * h->md), vpvs2(2 * n * h->md), org2;
+    MQ_CUDA(d2h(z2.data(), h->z, z2.size(), s));
+    MQ_CUDA(d2h(vp2.data(), h->vp, vp2.size(), s));
+    MQ_CUDA(d2h(vpvs2.data(), h->vpvs, vpvs2.size(), s));
+    if (m->origin) { org2.resize(2 * n * h->ne); MQ_CUDA(d2h(org2.data(), h->origin, org2.size(), s)); }
+    MQ_CUDA(cudaStreamSynchronize(s));
     for (size_t c = 0; c < n; c++) {
         const size_t mo = ((size_t)mcur[c] * n + c) * h->md;
         m->dim[c] = dim2[mcur[c] * n + c];
         if (m->dim[c] > m->max_dim) { set_error("mq_get_models: chain %zu has %d nuclei > max_dim %d", c, m->dim[c], m->max_dim); return MQ_ERR_ARG; }
-        MQ_CUDA(d2h(m->z + c * m->max_dim, h->z + mo, w, s));
-        MQ_CUDA(d2h(m->vp + c * m->max_dim, h->vp + mo, w, s));
-        MQ_CUDA(d2h(m->vpvs + c * m->max_dim, h->vpvs + mo, w, s));
-        if (m->origin) MQ_CUDA(d2h(m->origin + c * h->ne, h->origin + ((size_t)ecur[c] * n + c) * h->ne, h->ne, s));
+        memcpy(m->z + c * m->max_dim, z2.data() + mo, w * sizeof(float));
+        memcpy(m->vp + c * m->max_dim, vp2.data() + mo, w * sizeof(float));
+        memcpy(m->vpvs + c * m->max_dim, vpvs2.data() + mo, w * sizeof(float));
+        if (m->origin) memcpy(m->origin + c * h->ne, org2.data() + ((size_t)ecur[c] * n + c) * h->ne, h->ne * sizeof(float));
     }
     MQ_CUDA(d2h(m->eq, h->eq, n * h->ne * 3, s));
     MQ_CUDA(d2h(m->pres, h->pres, n * h->ns, s));

@@ -151,6 +151,8 @@ struct mq_batch {
     float* h_stage; size_t h_cap_floats;   // pinned, grown on demand
     cudaEvent_t ev_count, ev_data;
     int n_records, n_lost;
+    int delivered;          // records handed to the callback so far (a delivery that was stopped early can be resumed)
+    std::vector<int>* order;
 };
 namespace mq {
 struct Sampler : SamplerDev {
@@ -957,6 +959,7 @@ void sampler_destroy(Handle* h)
         if (b.h_stage) cudaFreeHost(b.h_stage);
         if (b.ev_count) cudaEventDestroy(b.ev_count);
         if (b.ev_data) cudaEventDestroy(b.ev_data);
+        delete b.order;
     }
     if (s->ev_main) cudaEventDestroy(s->ev_main);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -1306,7 +1309,7 @@ extern "C" int mq_drain_begin(mq_handle* hh, mq_batch** out)
     MQ_CUDA(cudaGetLastError());
     MQ_CUDA(cudaMemcpyAsync(b->h_count, b->d_count, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
     MQ_CUDA(cudaEventRecord(b->ev_count, cs));
-    b->state = 1; b->n_records = 0; b->n_lost = 0;
+    b->state = 1; b->n_records = 0; b->n_lost = 0; b->delivered = 0;
     *out = b;
     return MQ_OK;
 }
@@ -1347,14 +1350,21 @@ extern "C" int mq_batch_deliver(mq_batch* b, mq_record_fn fn, void* user)
     const Handle* h = b->h;
     // the pack kernel places the chains in the order its blocks arrive; deliver by chain number (a chain's records are
     // next to each other in the order they were produced, and the sort is stable)
-    std::vector<int> order((size_t)b->n_records);
-    for (int i = 0; i < b->n_records; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-        return ((const int32_t*)(b->h_stage + (size_t)x * b->rec_floats))[0] < ((const int32_t*)(b->h_stage + (size_t)y * b->rec_floats))[0];
-    });
-    for (int i = 0; i < b->n_records; i++) {
+    if (!b->order) b->order = new std::vector<int>();
+    std::vector<int>& order = *b->order;
+    if (b->delivered == 0) {
+        order.resize((size_t)b->n_records);
+        for (int i = 0; i < b->n_records; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            return ((const int32_t*)(b->h_stage + (size_t)x * b->rec_floats))[0] < ((const int32_t*)(b->h_stage + (size_t)y * b->rec_floats))[0];
+        });
+    }
+    // a callback that returns non-zero stops the delivery; the records not yet delivered stay in the batch and a further
+    // mq_batch_deliver call goes on with them (mq_batch_release discards them)
+    while (b->delivered < b->n_records) {
         mq_record r;
-        record_view(b->h_stage + (size_t)order[i] * b->rec_floats, h->md, h->ne, h->ns, &r);
+        record_view(b->h_stage + (size_t)order[b->delivered] * b->rec_floats, h->md, h->ne, h->ns, &r);
+        b->delivered++;
         if (fn(user, &r)) break;
     }
     return MQ_OK;
