@@ -535,9 +535,12 @@ EIK_HD float chain_a_node(ChainA& a, float pnext, float sk, bool& tie)
     const float dt2 = a.cn - a.pprev;
     est = a.cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
     cv = fminf(cv, in_zero_lim(dt2, lim) ? est : kInf);
-    cv = fminf(cv, a.pk + sk);
+    const float e3 = a.pk + sk;
+    cv = fminf(cv, e3);
     cv = fminf(cv, fmaf(a.sprev, kSqrt2, a.pprev));
-    const float cmin = fminf(kInf, a.pk + fminf(a.sprev, sk));   // == fmin_ref for the positive, non-NaN cell slownesses
+    // 1-D transmission in front of a minimum: pk + min(sprev, sk) = min(pk + sprev, pk + sk) (rounding is monotone), and
+    // it stays below INF at every real node (one of its two cells is real), so the reference's clip against INF is void
+    const float cmin = fminf(e3, a.pk + a.sprev);
     const float val = up ? cv : (root ? cmin : kInf);
     a.cn = val; a.pprev = a.pk; a.pk = pnext; a.sprev = sk;
     return val;
@@ -555,9 +558,10 @@ EIK_HD float chain_b_node(ChainB& b, float pprev, float hs1)
     const float dt2 = b.cn - b.pnx;
     est = b.cn + sqrt_pos(fmaf(-dt2, dt2, s0sq));
     cv = fminf(cv, in_zero_lim(dt2, lim) ? est : kInf);
-    cv = fminf(cv, b.pk + hs1);
+    const float e3 = b.pk + hs1;
+    cv = fminf(cv, e3);
     cv = fminf(cv, fmaf(b.s0, kSqrt2, b.pnx));
-    const float cmin = fminf(kInf, b.pk + fminf(hs1, b.s0));
+    const float cmin = fminf(e3, b.pk + b.s0);
     const float val = down ? cv : (root ? cmin : kInf);
     b.cn = val; b.pnx = b.pk; b.pk = pprev; b.s0 = hs1;
     return val;
@@ -619,15 +623,16 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
     };
     auto run_blocks = [&](int n_blocks, bool merge) {      // n_blocks blocks of four nodes per chain
         if (n_blocks <= 0) return;
-        Blk cur, nxt, nn;              // two blocks in flight behind the one being worked on
-        load4(cur, 0, merge);
-        if (n_blocks > 1) load4(nxt, 4, merge);
-        for (int blk = 0; blk < n_blocks; blk++) {
-            if (blk + 2 < n_blocks) load4(nn, 8, merge);
-            compute4(cur, merge);
-            cur = nxt;
-            nxt = nn;
+        Blk qa, qb;                    // ping-pong: one block is worked on while the other is in flight, no copies
+        load4(qa, 0, merge);
+        int blk = 0;
+        for (; blk + 2 <= n_blocks; blk += 2) {
+            load4(qb, 4, merge);
+            compute4(qa, merge);
+            if (blk + 2 < n_blocks) load4(qa, 4, merge);
+            compute4(qb, merge);
         }
+        if (blk < n_blocks) compute4(qa, merge);
     };
     struct No { enum { value = 0 }; };
     struct Yes { enum { value = 1 }; };

@@ -137,6 +137,8 @@ __device__ __forceinline__ bool tmem_sweep(bool need, uint32_t tp, uint32_t tc, 
     // chain A starts at node -1 (parent -2: nothing there), chain B at node CA-2 (parent CA-1: nothing there)
     eikf::ChainA a{2.0f * kEdge, r.pa_cur[0], kInf, kInf};
     eikf::ChainB b{4.0f * kEdge, r.pb_cur[3], kInf, kInf};
+    // (unrolling these loops by two saves the register copies between the group being worked on and the one being fetched,
+    //  7 % of the instructions, and measured 2 - 8 % SLOWER: profiles/README.md, r2unroll)
 #pragma unroll 1
     for (int j = 0; j < NB / 2; j++) tmem_group<NB, MASKED, false>(j, need, tp, tc, tS, a, b, r, tie);
     tmem_wait_st();                      // the other chain's stores must have landed before they are read back
