@@ -251,7 +251,9 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
     {
         // regrouping of the solves of a table rebuild (MCMCEQ_EIKONAL_ORDER=0 keeps the natural order)
         const char* e = getenv("MCMCEQ_EIKONAL_ORDER");
-        if (!(e && e[0] == '0') && h->nz <= 4096) {      // the sort key holds the source depth in 12 bits
+        // (planes that do not fit a shared-memory slice keep the natural order: a chain's P and S solves of one source
+        //  depth are neighbours there, which is the grouping their long box phases want; measured, tools/fine_probe2.py)
+        if (!(e && e[0] == '0') && eik_fast_supported(h->nxmod, h->nz)) {
             const int max_solves = 2 * n_chains * h->nz;
             h->eik_order_bytes = eik_order_bytes(max_solves);
             TRY(cudaMalloc(&h->eik_order_work, h->eik_order_bytes));

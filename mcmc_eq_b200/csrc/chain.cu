@@ -475,15 +475,19 @@ __global__ void propose_kernel(SamplerParams p, Handle hd, SamplerDev s, EvalVie
         // a proposal whose retry loop gave up (!ok) is rejected without being evaluated: it queues no table rebuild
         if (p.cfg.eikonal == 1 && p.cfg.aflag != 1 && ok) {
             const bool park = s.hold != nullptr;      // the tables are built later, together with those of other parked chains
+            // the rebuilds of one chain sit next to each other in the work list: its P and S solves of one source depth
+            // grow their boxes alike (same interfaces), which is what the lanes of a warp should have in common
+            int item = park ? 0 : atomicAdd(hd.n_items, (calct == 3) ? 2 : 1);
             for (int ph = 0; ph < 2; ph++) {
                 if (!(calct & (1 << ph))) continue;
                 const int tb = 1 - hd.tcur[2 * c + ph];
                 v.tbuf[2 * c + ph] = tb;
                 if (park) continue;
-                const int item = atomicAdd(hd.n_items, 1);
-                if (item >= 2 * n) continue;         // cannot happen (two items per chain at most); never write past the lists
-                hd.item_chain[item] = c; hd.item_phase[item] = ph;
-                hd.item_tab[item] = hd.tab + (((size_t)tb * n + c) * 2 + ph) * p.tab_stride;
+                if (item < 2 * n) {                  // cannot fail (two items per chain at most); never write past the lists
+                    hd.item_chain[item] = c; hd.item_phase[item] = ph;
+                    hd.item_tab[item] = hd.tab + (((size_t)tb * n + c) * 2 + ph) * p.tab_stride;
+                }
+                item++;
             }
             if (park && calct) s.hold[c] = 2;
         }
@@ -510,11 +514,12 @@ __global__ void flush_parked_kernel(SamplerParams p, Handle hd, SamplerDev s, Ev
     }
     s.hold[c] = 0;
     const int calct = s.rebuilt[c];
+    int item = calct ? atomicAdd(hd.n_items, (calct == 3) ? 2 : 1) : 0;
     for (int ph = 0; ph < 2; ph++) {
         if (!(calct & (1 << ph))) continue;
-        const int item = atomicAdd(hd.n_items, 1);
         hd.item_chain[item] = c; hd.item_phase[item] = ph;
         hd.item_tab[item] = hd.tab + (((size_t)v.tbuf[2 * c + ph] * p.n + c) * 2 + ph) * p.tab_stride;
+        item++;
     }
     if (s.todo[c] > 1) atomicAdd(&s.pass_stat[1], 1);
 }
@@ -555,13 +560,14 @@ __global__ void replay_setup_kernel(SamplerParams p, Handle hd, SamplerDev s, Ev
         v.mbuf[c] = mo; v.ev_only[c] = -1; v.ebuf[c] = 1 - ec;
         s.rebuilt[c] = calct;
         if (p.cfg.eikonal == 1 && p.cfg.aflag != 1) {
+            int item = atomicAdd(hd.n_items, (calct == 3) ? 2 : 1);
             for (int ph = 0; ph < 2; ph++) {
                 if (!(calct & (1 << ph))) continue;
                 const int tb = 1 - hd.tcur[2 * c + ph];
                 v.tbuf[2 * c + ph] = tb;
-                const int item = atomicAdd(hd.n_items, 1);
                 hd.item_chain[item] = c; hd.item_phase[item] = ph;
                 hd.item_tab[item] = hd.tab + (((size_t)tb * n + c) * 2 + ph) * p.tab_stride;
+                item++;
             }
         }
     }
