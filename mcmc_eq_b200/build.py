@@ -66,8 +66,19 @@ def build_emu(force: bool = False) -> str:
     out = os.path.join(ROOT, "tests", "emu", "libeik_emu.so")
     deps = [src, os.path.join(CSRC, "eik_core.cuh"), os.path.join(CSRC, "eik_fast.cuh")]
     if force or not _newer(out, deps):
-        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unused-but-set-variable",
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-but-set-variable",
                         src, "-o", out], check=True)
+    return out
+
+
+def build_emu_mt(force: bool = False) -> str:
+    """Host build of the warp-synchronous solver with a warp of host threads (tests/emu/host_warp.h), CPU tests only."""
+    src = os.path.join(ROOT, "tests", "emu", "eik_emu_mt.cpp")
+    out = os.path.join(ROOT, "tests", "emu", "libeik_emu_mt.so")
+    deps = [src, os.path.join(ROOT, "tests", "emu", "host_warp.h"), os.path.join(CSRC, "eik_core.cuh"), os.path.join(CSRC, "eik_fast.cuh")]
+    if force or not _newer(out, deps):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
+                        "-Wno-unused-but-set-variable", src, "-o", out], check=True)
     return out
 
 
@@ -82,6 +93,7 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
     build_host(force)          # before the oracle: oracle/_ref links the reference's drivers against the function-seam shim
     build_oracle(force)
     build_emu(force)
+    build_emu_mt(force)
 
 
 if __name__ == "__main__":

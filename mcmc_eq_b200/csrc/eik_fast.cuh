@@ -44,6 +44,9 @@ constexpr int LS = 32;   // lane stride of the interleaved arrays
 #define EIKF_SYNC() __syncwarp()
 #define EIKF_MIN(v) __reduce_min_sync(0xffffffffu, (v))
 #define EIKF_MAX(v) __reduce_max_sync(0xffffffffu, (v))
+#elif defined(EIKF_HOST_WARP)
+// tests/emu/eik_emu_mt.cpp: a "warp" of host threads in lock-step, collectives by barrier (defines LS and the four macros)
+#include EIKF_HOST_WARP
 #else
 constexpr int LS = 1;
 #define EIKF_ANY(p) (p)
@@ -56,9 +59,14 @@ struct Dims {
     int nx, nz;          // coarse plane
     int wx;              // columns of the global box window: min(nx, max(nz + 3, 13))
     int col_len;         // column buffer: indices -1 .. col_len (col_len >= max(nz, 43); -1 and nz hold sentinels)
-    int row_len;         // row buffer: top row from the front, bottom row from the back, never more than
-                         // nz + 3 nodes between them while both are needed; >= max(nz + 4, 48)
+    int row_len;         // row buffer: top row from the front, bottom row from the back.  While both are needed they hold
+                         // X1 + 1 nodes each, and X1 <= (nz + 2) / 2 then (a seed box that failed on both sides in the same
+                         // round of seed_search is 2.5 nodes wider than half its height): nz + 4 nodes for an even nz,
+                         // nz + 5 for an odd one (tests/test_emu_cpu.py: test_row_buffer_*); the refined grid needs 2 x 22
     int row_march;       // rows whose past times do not decrease away from the axis are swept in lock-step (row_march)
+    int lock_cols;       // shared-memory slice with a second column buffer: the columns of the growing box are swept by the
+                         // two-chain loop over the union of the lanes' ranges (as in GM mode) instead of the per-lane
+                         // in-place walk.  Faster box phases, fewer slices per SM: pays for launches a few tasks per warp deep
 };
 
 EIK_HD Dims make_dims(int nx, int nz)
@@ -68,14 +76,15 @@ EIK_HD Dims make_dims(int nx, int nz)
     D.wx = (nz + 3 > 13) ? nz + 3 : 13;
     if (D.wx > nx) D.wx = nx;
     D.col_len = nz > 43 ? nz : 43;
-    D.row_len = (nz + 4 > 48) ? nz + 4 : 48;
+    D.row_len = (nz + 4 + (nz & 1) > 48) ? nz + 4 + (nz & 1) : 48;
     D.row_march = 1;
+    D.lock_cols = 0;
     return D;
 }
-// floats per lane of the three shared arrays: S[-1..nz-1], COL[-1..col_len], ROW[0..row_len-1]
-EIK_HD int smem_floats_per_lane(const Dims& D) { return (D.nz + 1) + (D.col_len + 2) + D.row_len; }
-// the same plus the second column buffer of a slice in global memory (carve_global)
-EIK_HD int gmem_floats_per_lane(const Dims& D) { return smem_floats_per_lane(D) + (D.col_len + 2); }
+// floats per lane of the three shared arrays: S[-1..nz-1], COL[-1..col_len], ROW[0..row_len-1] (+ COL2 with lock_cols)
+EIK_HD int smem_floats_per_lane(const Dims& D) { return (D.nz + 1) + (D.col_len + 2) + D.row_len + (D.lock_cols ? D.col_len + 2 : 0); }
+// the same for a slice in global memory (carve_global): always with the second column buffer
+EIK_HD int gmem_floats_per_lane(const Dims& D) { return (D.nz + 1) + (D.col_len + 2) + D.row_len + (D.col_len + 2); }
 
 // One lane's view of the storage.
 struct Lane {
@@ -205,9 +214,10 @@ EIK_HD bool headwave_fires(float c, float cn, float hs2)
 // Returns true for lanes that must re-do the line on the slow path.
 // kedge (rows of the coarse grid only, else -1): node of the row whose cell on the far side along the row is the masked
 // dummy column (src/time_2d.c:489-496): the row reaches the right edge of the grid, X1 == mx.
+// report_ties (per lane, ping-pong discipline): return true where the in-place walk would.
 template <bool ROW>
 EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inplace, int kb, int ke, const Med& med,
-                       float c, float c2, float* Wt, long wstride, int* hint, int kedge = -1)
+                       float c, float c2, float* Wt, long wstride, int* hint, int kedge = -1, bool report_ties = false)
 {
     enum { SEG = 0, WALK = 1, DONE = 2 };
     const bool hw = ROW && (c2 < c);
@@ -273,7 +283,9 @@ EIK_HD bool fast_sweep(bool act, const float* P, float* C, int stride, bool inpl
                 }
             }
             if (ok) {
-                if (inplace && seen && eq_tail) slow = true;   // the walk would go on over overwritten values
+                // the walk would go on over overwritten values (report_ties: a ping-pong walk that tells where the in-place
+                // walk would have given up, so that its caller takes the slow path for the same lines)
+                if ((inplace || report_ties) && seen && eq_tail) slow = true;
                 const bool use3 = (d > 0) || (kk != 0);
                 float hs0, hs1;
                 if (ROW) { hs0 = c; hs1 = (d > 0 && kk == kedge) ? kInf : c; }
@@ -584,13 +596,15 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
     float* cb = C + (long)ke * LS;            // &C[kb]
 
     // one node of each chain; MERGE: the other chain has already been at these nodes
+    // (only lanes that take part write: in the pipelined kernel a lane whose box phase is over has handed its column on
+    //  in one of these buffers)
     auto step = [&](auto merge) {
         float a_val = chain_a_node(a, *pa, *sa, tie);
         if (decltype(merge)::value) a_val = fminf(a_val, *ca);
-        *ca = a_val;
+        if (act) *ca = a_val;
         float b_val = chain_b_node(b, *pb, *sb);
         if (decltype(merge)::value) b_val = fminf(b_val, *cb);
-        *cb = b_val;
+        if (act) *cb = b_val;
         pa += LS; sa += LS; ca += LS; pb -= LS; sb -= LS; cb -= LS;
     };
     // Columns in global memory (PF): four nodes of each chain per block, the operands of the NEXT block requested before
@@ -614,10 +628,9 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
             if (merge) {
                 a_val = fminf(a_val, q.ca[u]);
                 b_val = fminf(b_val, q.cb[u]);
-                if (Wt) { wt_store(Wt + (ca - C) + (long)u * LS, a_val); wt_store(Wt + (cb - C) - (long)u * LS, b_val); }
+                if (act && Wt) { wt_store(Wt + (ca - C) + (long)u * LS, a_val); wt_store(Wt + (cb - C) - (long)u * LS, b_val); }
             }
-            ca[(long)u * LS] = a_val;
-            cb[-(long)u * LS] = b_val;
+            if (act) { ca[(long)u * LS] = a_val; cb[-(long)u * LS] = b_val; }
         }
         pa += 4 * LS; sa += 4 * LS; ca += 4 * LS; pb -= 4 * LS; sb -= 4 * LS; cb -= 4 * LS;
     };
@@ -641,11 +654,11 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
     if (PF) {
         auto step_wt = [&]() {     // one node of each chain in the second half, with write-through
             float a_val = fminf(chain_a_node(a, *pa, *sa, tie), *ca);
-            *ca = a_val;
-            if (Wt) wt_store(Wt + (ca - C), a_val);
+            if (act) *ca = a_val;
+            if (act && Wt) wt_store(Wt + (ca - C), a_val);
             float b_val = fminf(chain_b_node(b, *pb, *sb), *cb);
-            *cb = b_val;
-            if (Wt) wt_store(Wt + (cb - C), b_val);
+            if (act) *cb = b_val;
+            if (act && Wt) wt_store(Wt + (cb - C), b_val);
             pa += LS; sa += LS; ca += LS; pb -= LS; sb -= LS; cb -= LS;
         };
         int i = 0;
@@ -653,7 +666,7 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
         i = (n1 / 4) * 4;
         for (; i < n1; i++) step(No());
         if (!(ke & 1)) {   // odd node count: both chains meet on the middle node, the second to arrive merges with the first
-            C[(long)(ke >> 1) * LS] = kInf;
+            if (act) C[(long)(ke >> 1) * LS] = kInf;
             step_wt();
             i++;
         }
@@ -664,7 +677,7 @@ EIK_HD bool march_sweep3(bool act, const float* P, float* C, const float* S, int
     } else {
 #pragma unroll 2
         for (int i = 0; i < n1; i++) step(No());
-        if (!(ke & 1)) C[(long)(ke >> 1) * LS] = kInf;   // odd node count: both chains meet on the middle node
+        if (act && !(ke & 1)) C[(long)(ke >> 1) * LS] = kInf;   // odd node count: both chains meet on the middle node
 #pragma unroll 2
         for (int i = n1; i <= ke; i++) step(Yes());
     }
@@ -752,7 +765,7 @@ EIK_HD bool row_ready(bool act, const float* R, int stride, int ke, bool known)
 // GM: the lane's arrays live in global memory (eik_fine_kernel): sweeps that run in lock-step read ahead, and a column of
 // the growing box is swept by the two-chain loop of the march (ping-pong between COL and COL2) whenever the lanes agree on
 // its range, instead of the per-lane in-place walk whose every step waits for a global load.
-template <bool FINE, bool GM>
+template <bool FINE, bool GM, bool LCT>
 // hand_col/hand_x1 (coarse grid only, may be nullptr): split mode.  A lane whose box spans the whole depth range
 // writes its right column (hand_col[k*32], k = 0..my) and X1 there and stops; a separate kernel marches on from it.
 EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMedium& cm, int j0, int hy, float* out,
@@ -769,10 +782,11 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
     bool boxphase = b.active && (b.Y0 > 0 || b.Y1 < b.my);
     float* col = L.COL;      // the lane's current right column
     // second column buffer (indices -1..ny): the idle row buffer once the rows are no longer needed, or COL2 (GM)
-    float* spare = GM ? L.COL2 : L.ROW + LS;
+    constexpr bool LC = GM || LCT;          // columns of the growing box by the two-chain loop (needs COL2)
+    float* spare = LC ? L.COL2 : L.ROW + LS;
     int hint = -1;           // first local minimum of the current column (known on the march)
     bool mono_top = false, mono_bot = false;   // the top / bottom row is known not to decrease away from the axis
-    if (GM && !FINE && b.active) {
+    if (LC && !FINE && b.active) {
         // both column buffers start as sentinels (see the column sweep below); the right column of the seed box is already
         // in COL (load_perimeter)
         for (int k = -1; k <= b.ny; k++) {
@@ -785,7 +799,7 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
     auto rowS = [&](int cy) -> float { return (!FINE && cy >= b.my) ? kInf : med.cell(cy); };
     const bool split = !FINE && hand_x1 != nullptr;
     auto hand_over = [&]() {     // this lane's box phase is over: the march kernel takes the column from here
-        for (int k = 0; k <= b.my; k++) hand_col[(size_t)k * 32] = col[(size_t)k * LS];
+        for (int k = 0; k <= b.my; k++) hand_col[(size_t)k * LS] = col[(size_t)k * LS];
         *hand_x1 = b.X1;
         b.active = 0;
     };
@@ -877,24 +891,37 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 if (need) line = ++b.X1;
                 const bool wt = need && (FINE || boxphase) && line < wx;
                 bool lockstep = false;
-                if (GM && !FINE) {
+                if (LC && !FINE) {
                     // The two-chain loop of the march over the union of the lanes' ranges.  Outside its own range a lane's
                     // column buffers hold sentinels that grow away from the source depth (gm_sentinel), so its chains start
                     // and end at its own Y0 and Y1 exactly as they do at the ends of a full column.
                     const int kb = EIKF_MIN(need ? b.Y0 : 0x7fffffff), ke = EIKF_MAX(need ? b.Y1 : -1);
                     lockstep = true;
-                    // (a lane writes through over the whole union range: window nodes outside its own box are untimed and
-                    //  are written again when a sweep of its own times them)
-                    const bool tie = march_sweep3<true>(need, col + (long)kb * LS, spare + (long)kb * LS, L.S + (long)kb * LS, ke - kb,
-                                                        wt ? T + ((size_t)line * b.ny + kb) * LS : nullptr);
+                    // (GM: a lane writes through over the whole union range: window nodes outside its own box are untimed
+                    //  and are written again when a sweep of its own times them)
+                    const bool tie = march_sweep3<GM>(need, col + (long)kb * LS, spare + (long)kb * LS, L.S + (long)kb * LS, ke - kb,
+                                                      (GM && wt) ? T + ((size_t)line * b.ny + kb) * LS : nullptr);
                     if (need) {   // what the sweep left outside this lane's range is not a column value: sentinels again
                         for (int k = kb; k < b.Y0; k++) spare[(long)k * LS] = gm_sentinel(k, b.ys);
                         for (int k = b.Y1 + 1; k <= ke; k++) spare[(long)k * LS] = gm_sentinel(k, b.ys);
                     }
-                    if (EIKF_ANY(tie))   // an exact tie in the past column: the literal walk, ping-pong discipline
-                        fast_sweep<false>(tie, col, spare, LS, false, b.Y0, b.Y1, med, 0.f, 0.f,
-                                          (tie && wt) ? T + (size_t)line * b.ny * LS : nullptr, LS, nullptr);
-                    if (need) { float* tmp = col; col = spare; spare = tmp; }
+                    // An exact tie in the past column (4 in 100 000): the lane's walk (fast_sweep), from the intact past column
+                    // into the other buffer.  In that discipline it reproduces every case of the reference's walk; a lane
+                    // whose box is still growing in shared memory reports the ties the in-place walk gives up on and re-does the
+                    // line on the window exactly where the in-place path does, so the two paths agree bit for bit on the device
+                    // as well (the generic sweep rounds its square roots correctly, the fast sweeps use MUFU.SQRT).
+                    bool s2 = false;
+                    if (EIKF_ANY(tie))
+                        s2 = fast_sweep<false>(tie, col, spare, LS, false, b.Y0, b.Y1, med, 0.f, 0.f,
+                                               (tie && wt) ? T + (size_t)line * b.ny * LS : nullptr, LS, nullptr, -1, !GM && wt);
+                    if (need) {
+                        float* tmp = col; col = spare; spare = tmp;
+                        if (!GM && wt && !tie) copy_strided(T + ((size_t)line * b.ny + b.Y0) * LS, LS, col + (long)b.Y0 * LS, LS, b.Y1 - b.Y0 + 1);
+                    }
+                    if (need && tie && s2) {
+                        const int rc = slow_line<0>(T, b, cm, L, RL, line, 1, b.Y0, b.Y1, true, col);
+                        if (rc != eik::kOk) status = rc;
+                    }
                 }
                 if (!lockstep) {
                     // While the box is growing the column is swept in place (the row buffer is busy and the window
@@ -984,7 +1011,7 @@ struct LaneTask {
     int* hand_x1;        // ... and the column index it belongs to (-1: nothing left to march); nullptr = fused mode
 };
 
-template <bool GM = false>
+template <bool GM = false, bool LCT = false>
 EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int* rows, int n_rows)
 {
     const int nx = D.nx, nz = D.nz, mx = nx - 1, my = nz - 1;
@@ -1059,7 +1086,7 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     EIKF_SYNC();
     // ---- refined grids of the lanes that need one
     if (EIKF_ANY(bf.active)) {
-        const int rc = run_grid<true, GM>(bf, L, D, cm, j0, hy, nullptr, 0, nullptr, 0, nullptr, nullptr);
+        const int rc = run_grid<true, GM, LCT>(bf, L, D, cm, j0, hy, nullptr, 0, nullptr, 0, nullptr, nullptr);
         if (rc != eik::kOk) status = rc;
         if (bf.active) {
             // every second fine node is a coarse node (src/time_2d.c:887-890); the fine field is complete in WF
@@ -1080,7 +1107,7 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     int xbox_end = -1;
     {
         if (t.hand_x1) *t.hand_x1 = -1;
-        const int rc = run_grid<false, GM>(bc, L, D, cm, 0, 0, t.out, t.out_rstride, rows, n_rows, t.full, &xbox_end, t.hand_col,
+        const int rc = run_grid<false, GM, LCT>(bc, L, D, cm, 0, 0, t.out, t.out_rstride, rows, n_rows, t.full, &xbox_end, t.hand_col,
                                        t.hand_x1);
         if (rc != eik::kOk) status = rc;
     }
@@ -1112,7 +1139,7 @@ EIK_HD void carve_shared(float* base, const Dims& D, Lane* L)
     L->S = base + (size_t)1 * LS;
     L->COL = L->S + (size_t)D.nz * LS + (size_t)1 * LS;
     L->ROW = L->COL + (size_t)(D.col_len + 1) * LS;
-    L->COL2 = nullptr;
+    L->COL2 = D.lock_cols ? L->ROW + (size_t)D.row_len * LS + (size_t)1 * LS : nullptr;
 }
 // the same for a slice in global memory, with the second column buffer behind the rows
 EIK_HD void carve_global(float* base, const Dims& D, Lane* L)

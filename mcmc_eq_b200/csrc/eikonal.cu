@@ -260,11 +260,12 @@ constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time 
 // two kernels bit for bit and guards this.
 // Arguments by value: as references they would live in the caller's stack frame and be re-read through it.
 // x1 receives the column at which the box phase ended (-1: nothing left to march).
+template <bool LC>
 __device__ __noinline__ int solve_warp_call(eikf::Dims D, eikf::Lane L, eikf::LaneTask t, const int* rows, int n_rows, int* x1_out)
 {
     int x1 = -1;
     t.hand_x1 = &x1;
-    const int rc = eikf::solve_warp(D, L, t, rows, n_rows);
+    const int rc = eikf::solve_warp<false, LC>(D, L, t, rows, n_rows);
     *x1_out = x1;
     return rc;
 }
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
             t.out = tab + (size_t)t.iz * b.xpitch;
             t.out_rstride = (long)nz * b.xpitch;
         }
-        const int rc = solve_warp_call(D, L, t, b.rows, b.n_rows, &x1);
+        const int rc = D.lock_cols ? solve_warp_call<true>(D, L, t, b.rows, b.n_rows, &x1) : solve_warp_call<false>(D, L, t, b.rows, b.n_rows, &x1);
         if (t.valid && b.status_min && rc < 0) atomicMin(b.status_min, rc);
         const bool live = x1 >= 0 && x1 < mx;
         if (!__any_sync(0xffffffffu, live)) { pipe_release(&ctl.slice_free, sl, lane); continue; }
@@ -446,7 +447,19 @@ bool eik_pipe_supported(int nxmod, int nz)
 cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t stream)
 {
     if (b.src_iz || b.full_out || !task_counter || !b.tie_scratch) return cudaErrorInvalidValue;
-    const eikf::Dims D = fast_dims(b.nxmod, b.nz);
+    eikf::Dims D = fast_dims(b.nxmod, b.nz);
+    {
+        // Lock-step columns in the box phase (a second column buffer per slice: 6 slices instead of 9 on the Example plane)
+        // pay while a launch is only a few tasks per warp deep: 8.68 -> 8.35 ms at 1024 chains (2.2 tasks per warp), but
+        // 15.27 -> 15.56 ms at 2048 and 55.6 -> 57.5 ms at 8192 (18 per warp), profiles/README.md r2lc.  MCMCEQ_PIPE_LC = 0 / 1 forces it off / on.
+        static int lc_env = -2;
+        if (lc_env == -2) { const char* e = getenv("MCMCEQ_PIPE_LC"); lc_env = e ? atoi(e) : -1; }
+        int sms_ = 148, dev_ = 0;
+        cudaGetDevice(&dev_);
+        cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
+        const long tasks = ((long)b.n_items * b.nz + 31) / 32;
+        D.lock_cols = (lc_env >= 0) ? (lc_env != 0) : (tasks <= 3L * sms_ * kPipeWarps);
+    }
     const size_t slice = fast_smem_floats_per_warp(D) * sizeof(float);
     const size_t tie = 0;      // the tie scratch lives in global memory (b.tie_scratch)
     int dev = 0, sms = 148, smem_max = 232448;

@@ -54,6 +54,31 @@ def test_full_tables_match_oracle(oracle, grid, kind, seed):
     assert stats.recursive_init > 0
 
 
+@pytest.mark.parametrize("nz", [61, 62, 63])
+def test_source_in_the_middle_of_its_layer_at_mid_depth(oracle, nz):
+    """The widest box the solver's shared row buffer has to hold (top and bottom row at full length in the same round): a
+    source in the middle of a layer that is itself in the middle of the depth range.  With a row buffer of nz + 4 nodes an
+    odd nz (the Example2 grid has 61) lost the top row's newest node to the bottom row's: 2.7 s off along the top of the
+    plane.  tests/test_emu_cpu.py holds the same case on the host build."""
+    import mcmc_eq_b200 as mq
+    nx = util.nxmod_of(util.EXAMPLE2_GRID)
+    mid = (nz - 1) // 2
+    slows, izs = [], []
+    for half in (7, 11, 12):
+        for iz in (mid - 1, mid, mid + 1):
+            s = np.full(nz, 0.1263643, np.float32)
+            s[:iz - half] = 0.2491149
+            s[iz - half:iz + half + 1] = 0.2100524
+            slows.append(s)
+            izs.append(iz)
+    t, st, rc = mq.eikonal_batch(np.array(slows), izs, nx, return_status=True)
+    assert rc == 0 and (st == 0).all()
+    for k in range(len(izs)):
+        tref, _ = util.oracle_time_2d(slows[k], nx, izs[k])
+        err = np.abs(t[k] - tref)
+        assert (err <= util.eikonal_tol(tref)).all(), (nz, izs[k], float(err.max()))
+
+
 def test_edge_grids_and_ragged_batches(oracle):
     import mcmc_eq_b200 as mq
     rng = np.random.default_rng(9)

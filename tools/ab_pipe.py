@@ -13,3 +13,7 @@ for pipe in ("0", "1"):
     res[pipe] = dict(np.load(path))
 bad = [k for k in res["0"] if not np.array_equal(res["0"][k], res["1"][k])]
 print("pipelined kernel differs from the fused kernel in:", bad if bad else "nothing")
+for k in bad:
+    a, b = res["0"][k], res["1"][k]
+    idx = np.argwhere(a != b)
+    print(k, len(idx), "of", a.size, "max |diff|", float(np.nanmax(np.abs(a.astype(float) - b.astype(float)))), "first", idx[:5].tolist())
