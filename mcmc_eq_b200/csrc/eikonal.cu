@@ -248,7 +248,10 @@ cudaError_t eik_order_tasks(const EikBatch& b, int32_t* order, void* work, size_
 // are in the latency-bound box phase and half in the issue-bound march, and there are 12 of them instead of 9 (with 154 registers each instead of 128: no spills).
 // Resources are taken in a fixed order (slice, then TMEM set; the tie scratch last and never while waiting for anything
 // else), holders of a TMEM set never wait for a slice: no cycle, no deadlock.
-constexpr int kPipeWarps = 12;     // measured 10 .. 20: 12 - 13 are best at 1024 chains, 12 - 16 equal at 8192 (profiles/README.md)
+#ifndef MCMCEQ_PIPE_WARPS
+#define MCMCEQ_PIPE_WARPS 12
+#endif
+constexpr int kPipeWarps = MCMCEQ_PIPE_WARPS;     // measured 10 .. 20: 12 - 13 are best at 1024 chains, 12 - 16 equal at 8192 (profiles/README.md)
 constexpr int kPipeCA = 64;          // nodes -1 .. 62 per TMEM column array: nz <= 62
 constexpr int kPipeMaxCtas = 256;    // one CTA per SM; the tie scratch is sized for this many
 constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time columns + slowness column of the tie scratch
@@ -260,8 +263,13 @@ constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time 
 // two kernels bit for bit and guards this.
 // Arguments by value: as references they would live in the caller's stack frame and be re-read through it.
 // x1 receives the column at which the box phase ended (-1: nothing left to march).
+#ifdef MCMCEQ_PIPE_INLINE      // A/B builds only (tools/ab_build.py): the variant that was wrong when it was last tried
+#define MQ_PIPE_CALL __forceinline__
+#else
+#define MQ_PIPE_CALL __noinline__
+#endif
 template <bool LC>
-__device__ __noinline__ int solve_warp_call(eikf::Dims D, eikf::Lane L, eikf::LaneTask t, const int* rows, int n_rows, int* x1_out)
+__device__ MQ_PIPE_CALL int solve_warp_call(eikf::Dims D, eikf::Lane L, eikf::LaneTask t, const int* rows, int n_rows, int* x1_out)
 {
     int x1 = -1;
     t.hand_x1 = &x1;

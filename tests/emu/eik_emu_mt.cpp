@@ -14,6 +14,12 @@
 using namespace eikf;   // LS and host_warp live in eikf (the header is included from inside it)
 
 extern "C" int emu_mt_lanes() { return EIKF_HOST_LANES; }
+// collectives that the lanes of the warp reached from different call sites since the library was loaded (must stay 0)
+extern "C" int emu_mt_site_mismatches() { return host_warp::team().mismatches.load(); }
+
+// what the scratch arrays hold before a solve (on the GPU: whatever the previous task left there)
+static float g_fill = 0.f;
+extern "C" void emu_mt_set_fill(float v) { g_fill = v; }
 
 // slow: [lanes][ny] slowness columns, iz: [lanes] source depths (-1: lane without a solve), full: [lanes][nx*ny] fields,
 // rows_out: [lanes][n_rows][nx], status: [lanes]
@@ -23,8 +29,8 @@ extern "C" void emu_mt_time_2d(const float* slow, int nx, int ny, const int* iz,
     constexpr int W = EIKF_HOST_LANES;
     eikf::Dims D = eikf::make_dims(nx, ny);
     D.lock_cols = (mode == 2) ? 1 : 0;
-    std::vector<float> SM((size_t)eikf::gmem_floats_per_lane(D) * W), Wn(((size_t)D.wx * ny) * W), WF((size_t)22 * 43 * W);
-    std::vector<float> hand((size_t)(ny + 2) * 3 * W);
+    std::vector<float> SM((size_t)eikf::gmem_floats_per_lane(D) * W, g_fill), Wn(((size_t)D.wx * ny) * W, g_fill), WF((size_t)22 * 43 * W, g_fill);
+    std::vector<float> hand((size_t)(ny + 2) * 3 * W, g_fill);
     auto body = [&](int lane) {
         eikf::host_warp::lane() = lane;
         eikf::Lane L;

@@ -14,6 +14,8 @@ struct Team {
     std::atomic<int> arrived{0};
     std::atomic<int> phase{0};
     int slot[EIKF_HOST_LANES];
+    int site[EIKF_HOST_LANES];      // source line of the collective each lane is at
+    std::atomic<int> mismatches{0}; // collectives that the lanes reached from different call sites (undefined on the GPU)
 };
 inline Team& team() { static Team t; return t; }
 inline int& lane() { static thread_local int l = 0; return l; }
@@ -31,21 +33,25 @@ inline void barrier()
     }
 }
 // op: 0 = any, 1 = min, 2 = max
-inline int reduce(int v, int op)
+inline int reduce(int v, int op, int site)
 {
     Team& t = team();
     t.slot[lane()] = v;
+    t.site[lane()] = site;
     barrier();
     int r = t.slot[0];
     for (int i = 1; i < EIKF_HOST_LANES; i++) {
         const int x = t.slot[i];
         r = (op == 0) ? (r | x) : (op == 1) ? (x < r ? x : r) : (x > r ? x : r);
+        if (lane() == 0 && t.site[i] != t.site[0]) t.mismatches.fetch_add(1);
     }
     barrier();
     return r;
 }
+inline void sync(int site) { reduce(0, 0, site); }
 }   // namespace host_warp
-#define EIKF_ANY(p) (host_warp::reduce((p) ? 1 : 0, 0) != 0)
-#define EIKF_SYNC() host_warp::barrier()
-#define EIKF_MIN(v) host_warp::reduce((v), 1)
-#define EIKF_MAX(v) host_warp::reduce((v), 2)
+// every lane of the warp must be at the SAME collective (on the GPU anything else is undefined): the call site is checked
+#define EIKF_ANY(p) (host_warp::reduce((p) ? 1 : 0, 0, __LINE__) != 0)
+#define EIKF_SYNC() host_warp::sync(__LINE__)
+#define EIKF_MIN(v) host_warp::reduce((v), 1, __LINE__)
+#define EIKF_MAX(v) host_warp::reduce((v), 2, __LINE__)
