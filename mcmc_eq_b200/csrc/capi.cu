@@ -98,6 +98,7 @@ extern "C" int mq_destroy(mq_handle* hh)
     profile_destroy(h);
     cudaFree(h->pk.ev_off); cudaFree(h->pk.n_p); cudaFree(h->pk.st_id); cudaFree(h->pk.r0); cudaFree(h->pk.cp);
     cudaFree(h->pk.x); cudaFree(h->pk.y); cudaFree(h->pk.t); cudaFree(h->pk.w1); cudaFree(h->pk.w2); cudaFree(h->pk.fix);
+    cudaFree(h->pk.rec4); cudaFree(h->pk.rec2);
     cudaFree(h->d_rows);
     free(h->rows_host);
     cudaFree(h->dim); cudaFree(h->mcur); cudaFree(h->tcur); cudaFree(h->ecur);
@@ -200,6 +201,25 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
     TRY(dalloc(&h->pk.t, np));          TRY(h2d(h->pk.t, pk->t, np, s));
     TRY(dalloc(&h->pk.w1, np));         TRY(h2d(h->pk.w1, w1.data(), np, s));
     TRY(dalloc(&h->pk.w2, np));         TRY(h2d(h->pk.w2, w2.data(), np, s));
+    {
+        std::vector<float4> rec4(np);
+        std::vector<float2> rec2(np);
+        for (int j = 0; j < np; j++) {
+            if (pk->st_id[j] < 0 || pk->st_id[j] >= (1 << 20) || r0[j] < 0 || r0[j] >= 256 || cp[j] < 0 || cp[j] >= 8) {
+                set_error("mq_create: pick %d does not fit the packed record (station %d, row %d, class %d)", j, pk->st_id[j], r0[j], cp[j]);
+                mq_destroy(hh);
+                return MQ_ERR_ARG;
+            }
+            const uint32_t code = (uint32_t)pk->st_id[j] | ((uint32_t)r0[j] << 20) | ((uint32_t)cp[j] << 28);
+            float cf;
+            memcpy(&cf, &code, sizeof cf);
+            rec4[j] = make_float4(pk->x[j], pk->y[j], pk->t[j], (float)w1[j]);
+            rec2[j] = make_float2((float)w2[j], cf);
+        }
+        TRY(dalloc(&h->pk.rec4, np));   TRY(h2d(h->pk.rec4, rec4.data(), np, s));
+        TRY(dalloc(&h->pk.rec2, np));   TRY(h2d(h->pk.rec2, rec2.data(), np, s));
+        TRY(cudaStreamSynchronize(s));
+    }
     TRY(dalloc(&h->pk.fix, 3 * (size_t)ne));
     {
         std::vector<double> fix(3 * (size_t)ne, -9999.0);

@@ -381,9 +381,15 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, 8) misfit_kernel(MisfitPara
     bool oob = false;         // a pick fell outside the table (1e30 sentinel of src/interpol.c:64-65)
     float* keep_l = &res_keep[KEEP ? wib : 0][0][lane];     // raw residual of this lane's i-th pick at keep_l[32 i]
 
+    // the pick's constants in two vector loads: (x, y, t, w1) and (w2, station | row << 20 | class << 28)
     auto one_pick = [&](int j) -> float {
         const int isS = ((j - b) >= npk) ? 1 : 0;
-        const float dx = __fsub_rn(p.pk.x[j], ex), dy = __fsub_rn(p.pk.y[j], ey);
+        const float4 r4 = __ldg(p.pk.rec4 + j);
+        const float2 r2 = __ldg(p.pk.rec2 + j);
+        const unsigned code = __float_as_uint(r2.y);
+        const int st = (int)(code & 0xfffffu), r0 = (int)((code >> 20) & 0xffu);
+        float corr = isS ? sres[st] : pres[st];
+        const float dx = __fsub_rn(r4.x, ex), dy = __fsub_rn(r4.y, ey);
         const float dist = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         float tt;
         if (RAY) {
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, 8) misfit_kernel(MisfitPara
             const bool out = wz.oob || m1 >= p.nxmod - 1;
             oob = oob || out;
             const float wa = __fsub_rn(__fmul_rn((float)(m1 + 1), p.hgrid), dist), wb = __fsub_rn(dist, __fmul_rn((float)m1, p.hgrid));
-            const float* q = (isS ? tabSz : tabPz) + (p.pk.r0[j] * rowsz + (out ? 0 : m1));
+            const float* q = (isS ? tabSz : tabPz) + (r0 * rowsz + (out ? 0 : m1));
             float t12[2];
 #pragma unroll
             for (int r = 0; r < 2; r++, q += rowsz) {
@@ -405,17 +411,15 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, 8) misfit_kernel(MisfitPara
                 s4 = __fadd_rn(s4, __fmul_rn(__fmul_rn(v4, wb), wz.d));
                 t12[r] = out ? 1e30f : __fmul_rn(pref0f, s4);
             }
-            tt = __fadd_rn(__fmul_rn(t12[0], p.pk.w1[j]), __fmul_rn(t12[1], p.pk.w2[j]));
+            tt = __fadd_rn(__fmul_rn(t12[0], r4.w), __fmul_rn(t12[1], r2.x));
         } else {
             const BilinearX w = bilinear_dist(wz, dist, p.hgrid, p.rh, false, p.nxmod);
             oob = oob || w.oob;
-            const float* row = (isS ? tabSz : tabPz) + p.pk.r0[j] * rowsz;
+            const float* row = (isS ? tabSz : tabPz) + r0 * rowsz;
             const float t1 = w.oob ? 1e30f : bilinear_eval(wz, w, row, p.xp);
             const float t2 = w.oob ? 1e30f : bilinear_eval(wz, w, row + rowsz, p.xp);
-            tt = __fadd_rn(__fmul_rn(t1, p.pk.w1[j]), __fmul_rn(t2, p.pk.w2[j]));
+            tt = __fadd_rn(__fmul_rn(t1, r4.w), __fmul_rn(t2, r2.x));
         }
-        const int st = p.pk.st_id[j];
-        float corr = isS ? sres[st] : pres[st];
         if (ridx >= 0) {
             const bool self = st == ridx;
             if (p.scor_flag <= 0) corr = self ? __fadd_rn(corr, isS ? rd1S : rd1P) : __fsub_rn(corr, isS ? rq1S : rq1P);
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, 8) misfit_kernel(MisfitPara
         if (corr < -1000.f) atomicOr(p.err, kErrStatcor);
         tt = __fadd_rn(tt, corr);
         if (p.tpred) p.tpred[(size_t)c * p.np + j] = tt;
-        return __fsub_rn(tt, p.pk.t[j]);
+        return __fsub_rn(tt, r4.z);
     };
 
 #pragma unroll 2
@@ -446,9 +450,32 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, 8) misfit_kernel(MisfitPara
         if (p.tpred) resid[j] = d;
         acc_l[p.pk.cp[j] * 32] += d * d;
     }
-    float acc[8];
+    // The eight class sums over the warp by recursive halving: at every step a lane hands the half of its values that its
+    // partner carries on with to that partner (8 -> 4 -> 2 -> 1 values per lane: 7 shuffles), two more steps sum the one value
+    // left over the four lanes that share it: 9 shuffles instead of 40.  Lane l ends up with the sum of class
+    // 4 * bit4(l) + 2 * bit3(l) + bit2(l); the order of the additions is fixed, so the sums are deterministic.
+    float cls_sum;
+    const int cls = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    {
+        float v[8], w4[4], w2v[2];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = warp_sum(acc_l[k * 32]);
+        for (int k = 0; k < 8; k++) v[k] = acc_l[k * 32];
+        const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float give = hi16 ? v[k] : v[k + 4];
+            w4[k] = (hi16 ? v[k + 4] : v[k]) + __shfl_xor_sync(0xffffffffu, give, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const float give = hi8 ? w4[k] : w4[k + 2];
+            w2v[k] = (hi8 ? w4[k + 2] : w4[k]) + __shfl_xor_sync(0xffffffffu, give, 8);
+        }
+        const float give = hi4 ? w2v[0] : w2v[1];
+        cls_sum = (hi4 ? w2v[1] : w2v[0]) + __shfl_xor_sync(0xffffffffu, give, 4);
+        cls_sum += __shfl_xor_sync(0xffffffffu, cls_sum, 2);
+        cls_sum += __shfl_xor_sync(0xffffffffu, cls_sum, 1);
+    }
     // With a 1e30 prediction in the event every de-meaned residual of it is ~1e29 or more and its
     // square overflows FP32 in the reference: the event's classes get an infinite misfit.  Stated
     // explicitly here because the overflow would otherwise depend on the summation order.
@@ -456,18 +483,16 @@ __global__ void __launch_bounds__(kMisfitWarps * 32, 8) misfit_kernel(MisfitPara
         unsigned present = 0u;    // classes that occur in this event
         for (int j = b + lane; j < end; j += 32) present |= 1u << p.pk.cp[j];
         present = __reduce_or_sync(0xffffffffu, present);
-#pragma unroll
-        for (int k = 0; k < 8; k++) if (present & (1u << k)) acc[k] = __int_as_float(0x7f800000);
+        if (present & (1u << cls)) cls_sum = __int_as_float(0x7f800000);
     }
-    if (lane == 0) {
+    if ((lane & 3) == 0) {      // one lane per class
         if (only >= 0) {
-            for (int k = 0; k < 8; k++) p.evq[8 * (size_t)c + k] = acc[k];
-            p.oq[c] = -mean;
+            p.evq[8 * (size_t)c + cls] = cls_sum;
+            if (lane == 0) p.oq[c] = -mean;
         } else {
             const int eb = p.v.ebuf[c];
-            float* o = p.evsum + (((size_t)eb * p.n + c) * p.ne + e) * 8;
-            for (int k = 0; k < 8; k++) o[k] = acc[k];
-            p.origin[((size_t)eb * p.n + c) * p.ne + e] = -mean;
+            p.evsum[(((size_t)eb * p.n + c) * p.ne + e) * 8 + cls] = cls_sum;
+            if (lane == 0) p.origin[((size_t)eb * p.n + c) * p.ne + e] = -mean;
         }
     }
 }

@@ -33,6 +33,9 @@ struct DevPicks {
     int32_t* r0;       // [np] index of the pick's receiver layer in the kept rows (layer+1 is r0+1)
     int32_t* cp;       // [np] 2*class + (phase == S)
     float *x, *y, *t, *w1, *w2;   // [np]
+    // the same per pick in two vector loads (misfit_kernel): rec4 = (x, y, t, w1), rec2 = (w2, bits of st_id | r0 << 20 | cp << 28)
+    float4* rec4;      // [np]
+    float2* rec2;      // [np]
     double* fix;       // [ne*3]
 };
 
