@@ -29,6 +29,9 @@
 // (bit-identical to the generic core on the host; on the device the radicands' square roots are MUFU.SQRT).
 #pragma once
 #include "eik_core.cuh"
+#ifdef EIKF_TRACE      // debug builds (tools/ab_build.py ... -DEIKF_TRACE=<solve>): one solve's box phase is printed
+#include <cstdio>
+#endif
 
 namespace eikf {
 
@@ -118,6 +121,9 @@ struct Box {
     // the window so far; the interior is filled when a slow path first needs the window (fill_seed_interior)
     int seed_pending, sX1, sY0, sY1;
     float shs0;
+#ifdef EIKF_TRACE
+    int trace;            // debug builds: this lane's solve is the one being traced (printf)
+#endif
 };
 
 // Square root of a stencil radicand.  On the device this is the hardware approximation (one MUFU.SQRT, relative
@@ -855,8 +861,21 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 // the coarse grid's last column of cells is masked (INF, src/time_2d.c:489-496): the last node of a row that
                 // reaches it has no cell beyond it; the refined grid is not masked (:466), its rows are uniform up to the edge
                 const bool edge = !FINE && b.X1 >= b.mx;
-                const float c = need ? rowS(line) : 1.f;
-                const float c2 = (need && line - 1 >= 0) ? rowS(line - 1) : kInf;   // far < 0: no head wave
+                // (The two slownesses are read through a volatile pointer on the coarse grid: with this function inlined into
+                //  eik_pipe_kernel nvcc 12.9 / ptxas gave c the value of c2 -- S[line - 1] instead of S[line], INF on the top
+                //  row -- at every optimisation level above -Xptxas -O1; found by printing one solve's box phase from both
+                //  kernels (-DEIKF_TRACE), profiles/README.md r2c.  tests/test_pipe_gpu.py compares the kernels bit for bit.)
+                float c = 1.f, c2 = kInf;      // c2 stays INF above the top row: no head wave there
+                if (need) {
+                    if (FINE) {
+                        c = rowS(line);
+                        if (line - 1 >= 0) c2 = rowS(line - 1);
+                    } else {
+                        const volatile float* sp = L.S + (long)line * LS;
+                        c = (line >= b.my) ? kInf : sp[0];
+                        if (line - 1 >= 0) c2 = sp[-(long)LS];
+                    }
+                }
                 const bool fastlane = need && !slow;
                 bool s2;
                 if (D.row_march && row_ready(fastlane, L.ROW, LS, b.X1, mono_top)) {
@@ -872,12 +891,18 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                                           T + (size_t)line * LS, (long)b.ny * LS, nullptr, edge ? b.X1 : -1);
                     mono_top = false;
                 }
+#ifdef EIKF_TRACE
+                if (!FINE && need && b.trace) printf("TR up line %d X1 %d slow %d s2 %d c %.6g c2 %.6g row[0] %.7g row[X1] %.7g win[0] %.7g\n", line, b.X1, (int)slow, (int)s2, c, c2, L.ROW[0], L.ROW[(size_t)b.X1 * LS], T[(size_t)line * LS]);
+#endif
                 if (need && (slow || s2)) {
                     const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, -1, 0, b.X1, refill, col)
                                         : slow_line<1>(T, b, cm, L, RL, line, -1, 0, b.X1, refill, col);
                     if (rc != eik::kOk) status = rc;
                     b.preset_up = 0;
                     mono_top = false;
+#ifdef EIKF_TRACE
+                    if (!FINE && b.trace) printf("TR up line %d after slow: row[0] %.7g row[X1] %.7g win[0] %.7g\n", line, L.ROW[0], L.ROW[(size_t)b.X1 * LS], T[(size_t)line * LS]);
+#endif
                 }
                 if (need) col[(size_t)line * LS] = L.ROW[(size_t)b.X1 * LS];
             }
@@ -959,8 +984,17 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                 bool slow = false;
                 if (need) line = ++b.Y1;
                 const bool edge = !FINE && b.X1 >= b.mx;
-                const float c = need ? rowS(line - 1) : 1.f;
-                const float c2 = need ? rowS(line) : kInf;
+                float c = 1.f, c2 = kInf;
+                if (need) {        // volatile on the coarse grid: see the row above the box
+                    if (FINE) {
+                        c = rowS(line - 1);
+                        c2 = rowS(line);
+                    } else {
+                        const volatile float* sp = L.S + (long)line * LS;
+                        c = sp[-(long)LS];                       // line - 1 < my always
+                        c2 = (line >= b.my) ? kInf : sp[0];
+                    }
+                }
                 float* bot = L.ROW + (size_t)(RL - 1) * LS;
                 const bool fastlane = need && !slow;
                 bool s2;
@@ -977,15 +1011,24 @@ EIK_HD int run_grid(Box& b, const Lane& L, const Dims& D, const eik::CoarseMediu
                                           T + (size_t)line * LS, (long)b.ny * LS, nullptr, edge ? b.X1 : -1);
                     mono_bot = false;
                 }
+#ifdef EIKF_TRACE
+                if (!FINE && need && b.trace) printf("TR dn line %d X1 %d slow %d s2 %d c %.6g c2 %.6g win1[0] %.7g win2[0] %.7g\n", line, b.X1, (int)slow, (int)s2, c, c2, T[(size_t)1 * LS], T[(size_t)2 * LS]);
+#endif
                 if (need && (slow || s2)) {
                     const int rc = FINE ? slow_line<1>(T, b, fm, L, RL, line, 1, 0, b.X1, !slow, col)
                                         : slow_line<1>(T, b, cm, L, RL, line, 1, 0, b.X1, !slow, col);
                     if (rc != eik::kOk) status = rc;
                     mono_bot = false;
+#ifdef EIKF_TRACE
+                    if (!FINE && b.trace) printf("TR dn line %d after slow: win1[0] %.7g win2[0] %.7g\n", line, T[(size_t)1 * LS], T[(size_t)2 * LS]);
+#endif
                 }
                 if (need) col[(size_t)line * LS] = L.ROW[(size_t)(RL - 1 - b.X1) * LS];
             }
         }
+#ifdef EIKF_TRACE
+        if (!FINE && b.active && b.trace) printf("TR round end X1 %d Y0 %d Y1 %d win1[0] %.7g win2[0] %.7g status %d\n", b.X1, b.Y0, b.Y1, T[(size_t)1 * LS], T[(size_t)2 * LS], status);
+#endif
         if (b.active && boxphase && b.Y0 == 0 && b.Y1 == b.my) {
             boxphase = false;            // from here on the solve is a march over columns
             if (xbox_end) *xbox_end = b.X1;
@@ -1009,6 +1052,9 @@ struct LaneTask {
     float* full;         // whole field in the reference layout x*nz+y (or nullptr)
     float* hand_col;     // split mode: where the box phase leaves its last column (element k at [k*32]) ...
     int* hand_x1;        // ... and the column index it belongs to (-1: nothing left to march); nullptr = fused mode
+#ifdef EIKF_TRACE
+    int trace;
+#endif
 };
 
 template <bool GM = false, bool LCT = false>
@@ -1026,7 +1072,13 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     Box bc;   // coarse box
     bc.nx = nx; bc.ny = nz; bc.mx = mx; bc.my = my; bc.ys = t.iz; bc.X1 = 0; bc.Y0 = 0; bc.Y1 = 0; bc.preset_up = 0; bc.active = 0;
     bc.seed_pending = 0; bc.sX1 = 0; bc.sY0 = 0; bc.sY1 = 0; bc.shs0 = 0.f;
+#ifdef EIKF_TRACE
+    bc.trace = 0;
+#endif
     Box bf = bc;   // refined box
+#ifdef EIKF_TRACE
+    bc.trace = t.valid ? t.trace : 0;
+#endif
     int j0 = 0, hy = 0;
     bool whole = false;
     float hs0 = 0.f;
@@ -1113,6 +1165,9 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
     }
     // ---- the part of the output that was computed while the box was still growing (it may have been
     //      re-timed by reverse propagation until the very end of that phase) comes from the window
+#ifdef EIKF_TRACE
+    if (t.valid && t.trace) printf("TR out whole %d xbox_end %d rows %d %d win1[0] %.7g win2[0] %.7g\n", (int)whole, xbox_end, rows[0], n_rows > 1 ? rows[1] : -1, L.W[(size_t)1 * LS], L.W[(size_t)2 * LS]);
+#endif
     if (t.valid && !whole) {
         if (t.out)
             for (int r = 0; r < n_rows; r++)

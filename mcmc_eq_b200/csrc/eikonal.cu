@@ -143,6 +143,9 @@ __device__ __forceinline__ void eik_fast_body(const EikBatch& b, const eikf::Dim
             }
             if (b.full_out) t.full = b.full_out + (size_t)g * nodes;
         }
+#ifdef EIKF_TRACE
+        t.trace = (g == EIKF_TRACE);
+#endif
         const int rc = eikf::solve_warp<GLOBAL_SLICE>(D, L, t, b.rows, b.n_rows);
         if (t.valid) {
             if (b.status) b.status[g] = rc;
@@ -256,17 +259,19 @@ constexpr int kPipeCA = 64;          // nodes -1 .. 62 per TMEM column array: nz
 constexpr int kPipeMaxCtas = 256;    // one CTA per SM; the tie scratch is sized for this many
 constexpr size_t kPipeTieFloats = (size_t)(3 * kPipeCA + 2) * 32;   // two time columns + slowness column of the tie scratch
 
-// The box phase of a task, compiled as a function of its own.  Inlined into eik_pipe_kernel next to the tensor-memory
-// march, nvcc 12.9 produced a kernel whose box-region output depended on unrelated code in run_grid (receiver row 0 left
-// at INF; found when the lock-step row sweeps were added, bisected on the GPU: any variant with the call inlined and the
-// top-row site present failed, every variant with the call out of line passed).  tests/test_pipe_gpu.py compares the
-// two kernels bit for bit and guards this.
+// The box phase of a task.  Until round 2 it had to be compiled as a function of its own: inlined next to the tensor-memory
+// march, nvcc 12.9 produced a kernel whose box-region output was wrong (bisected on the GPU in round 1: any variant with the
+// call inlined and the top-row site of run_grid present failed).  Printing one solve's box phase from both kernels
+// (-DEIKF_TRACE) showed what goes wrong: at that site the row's own strip slowness c came out as the far side's c2.  With the
+// two reads volatile (eik_fast.cuh, run_grid) the inlined kernel is bit-identical to the fused one and 8 % faster (LDS / STS
+// instead of generic loads and stores); tests/test_pipe_gpu.py compares the two kernels bit for bit on four model families
+// and guards this.  -DMCMCEQ_PIPE_NOINLINE restores the out-of-line call.
 // Arguments by value: as references they would live in the caller's stack frame and be re-read through it.
 // x1 receives the column at which the box phase ended (-1: nothing left to march).
-#ifdef MCMCEQ_PIPE_INLINE      // A/B builds only (tools/ab_build.py): the variant that was wrong when it was last tried
-#define MQ_PIPE_CALL __forceinline__
-#else
+#ifdef MCMCEQ_PIPE_NOINLINE
 #define MQ_PIPE_CALL __noinline__
+#else
+#define MQ_PIPE_CALL __forceinline__
 #endif
 template <bool LC>
 __device__ MQ_PIPE_CALL int solve_warp_call(eikf::Dims D, eikf::Lane L, eikf::LaneTask t, const int* rows, int n_rows, int* x1_out)
@@ -362,6 +367,9 @@ __global__ void __launch_bounds__(kPipeWarps * 32, 1) eik_pipe_kernel(EikBatch b
             t.out = tab + (size_t)t.iz * b.xpitch;
             t.out_rstride = (long)nz * b.xpitch;
         }
+#ifdef EIKF_TRACE
+        t.trace = (g == EIKF_TRACE);
+#endif
         const int rc = D.lock_cols ? solve_warp_call<true>(D, L, t, b.rows, b.n_rows, &x1) : solve_warp_call<false>(D, L, t, b.rows, b.n_rows, &x1);
         if (t.valid && b.status_min && rc < 0) atomicMin(b.status_min, rc);
         const bool live = x1 >= 0 && x1 < mx;

@@ -8,15 +8,17 @@ sys.path.insert(0, %r)
 import mcmc_eq_b200 as mq
 from tests import inputs, fwd_helpers as fh
 d = tempfile.mkdtemp(prefix="mqdr_")
-cfgp, pkp = inputs.materialise("example2", d)
+import os
+name = os.environ.get("DIAG_SET", "example2")
+cfgp, pkp = inputs.materialise(name, d)
 cfg, pk = mq.read_config(cfgp), mq.Picks.read(pkp)
 n = 1230
 smp = mq.Sampler(cfg, pk, n, 0, 1)
 rng = np.random.default_rng(4)
-st = fh.random_states(rng, cfg, pk, n, kind="lvz")
+st = fh.random_states(rng, cfg, pk, n, kind="lvz" if name == "example2" else "posterior")
 smp.forward_host(fh.fill_models(smp.new_models(32), st), 3)
 out = {}
-for c in (0, 3, 700):
+for c in (0, 1, 4, 700):
     for ph in (1, 2):
         t, idx = smp.rows(c, ph)
         out[f"t{c}_{ph}"] = t; out["idx"] = idx
