@@ -465,16 +465,13 @@ cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t s
     if (b.src_iz || b.full_out || !task_counter || !b.tie_scratch) return cudaErrorInvalidValue;
     eikf::Dims D = fast_dims(b.nxmod, b.nz);
     {
-        // Lock-step columns in the box phase (a second column buffer per slice: 6 slices instead of 9 on the Example plane)
-        // pay while a launch is only a few tasks per warp deep: 8.68 -> 8.35 ms at 1024 chains (2.2 tasks per warp), but
-        // 15.27 -> 15.56 ms at 2048 and 55.6 -> 57.5 ms at 8192 (18 per warp), profiles/README.md r2lc.  MCMCEQ_PIPE_LC = 0 / 1 forces it off / on.
+        // Lock-step columns in the box phase (a second column buffer per slice: 6 slices instead of 9 on the Example plane).
+        // Kernel ms per launch at 1024 / 2048 / 4096 / 8192 chains with the box phase inlined: 7.70 / 13.99 / 26.42 / 51.07
+        // against 8.03 / 14.24 / 26.66 / 51.07 with the per-lane in-place walk (profiles/README.md r2c).  MCMCEQ_PIPE_LC=0
+        // selects the in-place walk.
         static int lc_env = -2;
         if (lc_env == -2) { const char* e = getenv("MCMCEQ_PIPE_LC"); lc_env = e ? atoi(e) : -1; }
-        int sms_ = 148, dev_ = 0;
-        cudaGetDevice(&dev_);
-        cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
-        const long tasks = ((long)b.n_items * b.nz + 31) / 32;
-        D.lock_cols = (lc_env >= 0) ? (lc_env != 0) : (tasks <= 3L * sms_ * kPipeWarps);
+        D.lock_cols = (lc_env >= 0) ? (lc_env != 0) : 1;
     }
     const size_t slice = fast_smem_floats_per_warp(D) * sizeof(float);
     const size_t tie = 0;      // the tie scratch lives in global memory (b.tie_scratch)
