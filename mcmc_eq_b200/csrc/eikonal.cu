@@ -465,7 +465,7 @@ cudaError_t eik_launch_pipe(const EikBatch& b, int* task_counter, cudaStream_t s
     if (b.src_iz || b.full_out || !task_counter || !b.tie_scratch) return cudaErrorInvalidValue;
     eikf::Dims D = fast_dims(b.nxmod, b.nz);
     {
-        // Lock-step columns in the box phase (a second column buffer per slice: 6 slices instead of 9 on the Example plane).
+        // Lock-step columns in the box phase (a second column buffer per slice: 7 slices instead of 9 on the Example plane).
         // Kernel ms per launch at 1024 / 2048 / 4096 / 8192 chains with the box phase inlined: 7.70 / 13.99 / 26.42 / 51.07
         // against 8.03 / 14.24 / 26.66 / 51.07 with the per-lane in-place walk (profiles/README.md r2c).  MCMCEQ_PIPE_LC=0
         // selects the in-place walk.
