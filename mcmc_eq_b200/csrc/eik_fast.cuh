@@ -1089,17 +1089,16 @@ EIK_HD int solve_warp(const Dims& D, const Lane& L, const LaneTask& t, const int
         hs0 = eik::source_slowness(g);
         whole = (kind == eik::kSeedBox && g.X1 == mx && g.Y0 == 0 && g.Y1 == my);
         if (!whole) {
-            if (GM) {
+            {
                 // Only what can be read before a sweep writes it has to start as INF: the nodes round the source that the
                 // minimal initialisation and the copy-back of the refined grid leave untimed.  Everything else in the window
-                // is written through when it is timed (a window of the fine grid is 4.5 MB per lane).
+                // is written through when it is timed and never read before (a window of the fine grid is 4.5 MB per lane;
+                // on the Example plane clearing all of it was 2 GB of stores per launch of 1024 chains).  The host builds
+                // start from windows full of NaN (tests/test_emu_cpu.py).
                 const int xc = (D.wx - 1 < kInitMin + 2) ? D.wx - 1 : kInitMin + 2;
                 const int ylo = (t.iz - kInitMin - 2 > 0) ? t.iz - kInitMin - 2 : 0, yhi = (t.iz + kInitMin + 2 < my) ? t.iz + kInitMin + 2 : my;
                 for (int x = 0; x <= xc; x++)
                     for (int y = ylo; y <= yhi; y++) L.W[((size_t)x * nz + y) * LS] = kInf;
-            } else {
-                const int wn = D.wx * nz;
-                for (int i = 0; i < wn; i++) L.W[(size_t)i * LS] = kInf;
             }
             bc.active = 1;
         }

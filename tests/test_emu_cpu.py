@@ -194,7 +194,7 @@ def test_a_warp_of_lanes_is_bit_identical_to_the_generic_core(emu, emu_mt, mode,
     rng = np.random.default_rng(100 + 10 * mode + split)
     rows = np.array([0, 1, 2, nz - 1], np.int32)
     # the scratch arrays start as garbage (on the GPU: what the previous task left): nothing may depend on it
-    emu_mt.emu_mt_set_fill(float("nan") if split else 7.25)
+    emu_mt.emu_mt_set_fill(float("nan") if (split or mode != 1) else 7.25)
     for trial, kind in enumerate(["lvz", "posterior", "contrast"]):
         S = np.zeros((W, nz), np.float32)
         for l in range(W):
