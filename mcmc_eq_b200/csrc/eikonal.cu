@@ -245,10 +245,10 @@ cudaError_t eik_order_tasks(const EikBatch& b, int32_t* order, void* work, size_
 // ---- the pipelined kernel: box phase in shared memory, march in tensor memory, in ONE persistent CTA per SM --------------
 // The fused kernel holds 9 warps per SM because every warp keeps 24.7 KB of shared memory for its whole life, although it
 // only needs it for the box phase (per-lane indices); the march (warp-uniform indices) can live in TMEM.  Here 12 warps
-// per SM share kSlices shared-memory slices and 8 TMEM sets (past column, current column, slowness column = 3 x 64
+// per SM share the shared-memory slices (7 with the second column buffer of the lock-step box phase, Dims::lock_cols) and 8 TMEM sets (past column, current column, slowness column = 3 x 64
 // columns; two sets per lane quarter): a warp takes a slice for the box phase of a task, moves the task's last column and
 // slowness column into a TMEM set, gives the slice back and marches in tensor memory.  At any time about half of the warps
-// are in the latency-bound box phase and half in the issue-bound march, and there are 12 of them instead of 9 (with 154 registers each instead of 128: no spills).
+// are in the latency-bound box phase and half in the issue-bound march, and there are 12 of them instead of 9 (146 registers each: no spills).
 // Resources are taken in a fixed order (slice, then TMEM set; the tie scratch last and never while waiting for anything
 // else), holders of a TMEM set never wait for a slice: no cycle, no deadlock.
 #ifndef MCMCEQ_PIPE_WARPS
