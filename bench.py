@@ -609,8 +609,8 @@ def main():
     smp = mq.Sampler(cfg, pk, chains, device, 1000)
     smp.set_chain_offset(rank * chains)     # chain g of the job draws from stream (seed, g) on whichever GPU it runs
     smp.init_chains()
-    # leave the start phase of the chain the way a real run does: a few hundred mixed iterations are not needed for
-    # timing (the cost of a 'P' step does not depend on the state), but the models must be valid chain states
+    # the timed steps start from valid chain states W proposals away from the start models, as a fresh reference chain does
+    # (the reference arm times fresh chains too); "p_full_after_mixing" repeats the measurement on burned-in chains
     for _ in range(W):
         smp.step(1, args.proposals)
     smp.sync()
@@ -647,6 +647,23 @@ def main():
     extras = {}
     if not args.no_extras:
         extras["p_mix"] = pmix_block(smp, dist, device, chains, n_gpus)
+        if n_gpus == 1 and set(args.proposals) <= {"P"}:
+            # The headline is timed on chains a few proposals away from their start models (prior-like, median RMS of
+            # seconds: high contrasts, low-velocity zones, the solver's slow path in most warps).  The same P_full step on
+            # the chains after the mixed iterations above plus 1500 more (posterior-like models), for comparison.
+            smp.step(1500, None)
+            k2 = max(3, min(args.steps, 20))
+            ms2, e2, n2, _spl2, kern2 = timed_steps(smp, dist, device, k2, 1, "P")
+            extras["p_full_after_mixing"] = {"value": chains * k2 / (ms2 / 1000.0), "unit": UNIT, "steps": k2, "ms_per_step": ms2 / k2,
+                                             "eikonal_ms_per_launch": e2 / max(n2, 1), "mixed_iterations_before": 48 + 480 + 1500,
+                                             "median_rms_s": float(np.median(smp.stats()[2])),
+                                             "kernels_launched": {k: v[0] for k, v in kern2.items()}}
+            if roofline and n2 > 0:
+                t2 = e2 / n2 / 1000.0
+                peak2, _src2 = measured_peak()
+                extras["p_full_after_mixing"]["roofline"] = {
+                    "hbm_algorithmic_frac": roofline["algorithmic_bytes_per_solve"] * roofline["solves_per_launch"] / t2 / 1e9 / peak2,
+                    "smem_algorithmic_frac": 32.0 * smp.nxmod * cfg.grid.nz * roofline["solves_per_launch"] / t2 / 1e9 / SMEM_PEAK_GBS}
         if dist is not None:
             extras["collectives"] = collectives_block(pk, dist, rank, world, device, 1000)
     base = None
