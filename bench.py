@@ -648,15 +648,18 @@ def main():
     if not args.no_extras:
         extras["p_mix"] = pmix_block(smp, dist, device, chains, n_gpus)
         if n_gpus == 1 and set(args.proposals) <= {"P"}:
-            # The headline is timed on chains a few proposals away from their start models (prior-like, median RMS of
-            # seconds: high contrasts, low-velocity zones, the solver's slow path in most warps).  The same P_full step on
-            # the chains after the mixed iterations above plus 1500 more (posterior-like models), for comparison.
+            # The work of a solve depends on the model (number of layers, contrasts: a one-layer model is a homogeneous
+            # medium with analytic solves).  The headline is timed on chains a few proposals away from their start models, as
+            # a fresh reference chain is; the same P_full step on the same chains after the mixed iterations above plus 1500
+            # more, with the mean number of layers next to it, shows how much that matters.
             smp.step(1500, None)
             k2 = max(3, min(args.steps, 20))
             ms2, e2, n2, _spl2, kern2 = timed_steps(smp, dist, device, k2, 1, "P")
             extras["p_full_after_mixing"] = {"value": chains * k2 / (ms2 / 1000.0), "unit": UNIT, "steps": k2, "ms_per_step": ms2 / k2,
                                              "eikonal_ms_per_launch": e2 / max(n2, 1), "mixed_iterations_before": 48 + 480 + 1500,
                                              "median_rms_s": float(np.median(smp.stats()[2])),
+                                             "mean_layers": float(np.mean(smp.get_models().dim)),
+                                             "mean_layers_headline": float(np.mean(m_host.dim)),
                                              "kernels_launched": {k: v[0] for k, v in kern2.items()}}
             if roofline and n2 > 0:
                 t2 = e2 / n2 / 1000.0
