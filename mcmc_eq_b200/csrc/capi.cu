@@ -287,7 +287,9 @@ extern "C" int mq_create(const mq_config* cfg, const mq_picks* pk, int n_chains,
     return MQ_OK;
 }
 
-extern "C" int mq_set_models(mq_handle* hh, const mq_models* m)
+// sync: wait for the copies before returning (the caller may reuse its buffers at once); mq_forward_host goes on enqueueing
+// the forward on the same stream and waits once, for the results
+static int set_models(mq_handle* hh, const mq_models* m, bool sync)
 {
     if (!hh || !m) { set_error("mq_set_models: null"); return MQ_ERR_ARG; }
     Handle* h = &hh->h;
@@ -313,11 +315,12 @@ extern "C" int mq_set_models(mq_handle* hh, const mq_models* m)
     MQ_CUDA(h2d(h->pres, m->pres, n * h->ns, s));
     MQ_CUDA(h2d(h->sres, m->sres, n * h->ns, s));
     MQ_CUDA(h2d(h->noise, m->noise, n * 8, s));
-    MQ_CUDA(cudaStreamSynchronize(s));
+    if (sync) MQ_CUDA(cudaStreamSynchronize(s));
     h->models_set = true;
     h->forward_done = false;
     return MQ_OK;
 }
+extern "C" int mq_set_models(mq_handle* hh, const mq_models* m) { return set_models(hh, m, true); }
 
 extern "C" int mq_get_models(mq_handle* hh, mq_models* m)
 {
@@ -438,12 +441,15 @@ int forward_current_device(Handle* h, int calct)
 }
 }  // namespace mq
 
-static int copy_forward_results(Handle* h, float* mf, float* origin)
+// ecur_zero: every chain's current event buffer is 0 (right after mq_set_models): no need to ask the device first
+static int copy_forward_results(Handle* h, float* mf, float* origin, bool ecur_zero = false)
 {
     cudaStream_t s = h->stream;
     const size_t n = h->n;
     if (mf) MQ_CUDA(d2h(mf, h->mf, n * 8, s));
-    if (origin) {
+    if (origin && ecur_zero) {
+        MQ_CUDA(d2h(origin, h->origin, n * h->ne, s));
+    } else if (origin) {
         std::vector<int32_t> ecur(n);
         MQ_CUDA(d2h(ecur.data(), h->ecur, n, s));
         MQ_CUDA(cudaStreamSynchronize(s));
@@ -470,9 +476,14 @@ extern "C" int mq_forward(mq_handle* hh, int calct, float* mf, float* origin)
 
 extern "C" int mq_forward_host(mq_handle* hh, const mq_models* m, int calct, float* mf, float* origin)
 {
-    const int rc = mq_set_models(hh, m);
+    if (!hh || calct < 0 || calct > 3) { set_error("mq_forward_host: bad argument"); return MQ_ERR_ARG; }
+    // one pass down the stream: models in, forward, results out, one wait at the end (check_device_errors)
+    int rc = set_models(hh, m, false);
     if (rc != MQ_OK) return rc;
-    return mq_forward(hh, calct, mf, origin);
+    Handle* h = &hh->h;
+    rc = forward_current_device(h, calct);
+    if (rc != MQ_OK) { cudaStreamSynchronize(h->stream); return rc; }
+    return copy_forward_results(h, mf, origin, true);
 }
 
 // Host-driven use (a reference-style main that calls mq_forward_host per proposal): the device tables are those of
