@@ -222,3 +222,31 @@ def test_a_warp_of_lanes_is_bit_identical_to_the_generic_core(emu, emu_mt, mode,
                     assert np.array_equal(full[l].view(np.uint32), t.view(np.uint32)), (kind, iz, l)
     # every collective was reached by all lanes from the same call site (anything else is undefined on the GPU)
     assert emu_mt.emu_mt_site_mismatches() == 0
+
+
+def test_a_warp_of_lanes_on_the_example_plane(emu, emu_mt):
+    """The benched configuration of the pipelined kernel (lock-step box-phase columns, hand-over to the march) on the Example
+    plane (282 x 62, even nz) with eight posterior-like models per warp: identical bits to the one-lane generic core."""
+    ip = C.POINTER(C.c_int)
+    W = emu_mt.emu_mt_lanes()
+    g = util.EXAMPLE_GRID
+    nx, nz, h, z0 = util.nxmod_of(g), g["nz"], g["h"], g["z0"]
+    rng = np.random.default_rng(7)
+    rows = np.array([1, 2], np.int32)
+    emu_mt.emu_mt_set_fill(float("nan"))
+    S = np.zeros((W, nz), np.float32)
+    for l in range(W):
+        z, vp, vpvs = util.voronoi_model(rng, int(rng.integers(1, 8)), z0, z0 + (nz - 1) * h, "posterior" if l % 2 else "lvz")
+        S[l] = util.rasterise_np(z, vp, vpvs, h, z0, nz, 1 + l % 2)
+    for iz in (0, 7, 19, 30, 31, 44, nz - 1):
+        izs = np.full(W, iz, np.int32)
+        full = np.zeros((W, 1), np.float32)
+        ro = np.zeros((W, len(rows), nx), np.float32)
+        st = np.zeros(W, np.int32)
+        emu_mt.emu_mt_time_2d(ptr(S), nx, nz, izs.ctypes.data_as(ip), ptr(full), rows.ctypes.data_as(ip), len(rows), ptr(ro),
+                              st.ctypes.data_as(ip), 2, 1)
+        for l in range(W):
+            t, rc, _ = _run(emu, S[l], nx, iz)
+            assert rc == 0 and st[l] == 0
+            assert np.array_equal(ro[l].view(np.uint32), t[:, rows].T.view(np.uint32)), (iz, l, float(np.abs(ro[l] - t[:, rows].T).max()))
+    assert emu_mt.emu_mt_site_mismatches() == 0
