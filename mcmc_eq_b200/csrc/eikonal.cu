@@ -208,7 +208,16 @@ __global__ void eik_key_kernel(EikBatch b, int max_solves, uint64_t* keys, int32
     // half-width of the seed box first: it decides the kind of initialisation (src/time_2d.c:682-711)
     const uint64_t wd = (d0 == 31) ? 15 : (d0 >> 1), wu = (u0 == 31) ? 15 : (u0 >> 1), w = wd < wu ? wd : wu;
     (void)u2;
-    keys[g] = ((uint64_t)iz << 32) | (w << 28) | (d0 << 23) | (u0 << 18) | (d1 << 13) | (u1 << 8) | (d2 << 3);
+#if defined(MCMCEQ_ORDER_EDGES_FIRST)      // A/B builds: source depths from the edges of the depth range inwards (long box phases first)
+    const int zk = (iz <= my / 2) ? 2 * iz : 2 * (my - iz) + 1;
+#elif defined(MCMCEQ_ORDER_INTERLEAVE)     // upper and lower half of the depth range alternately: long and short box phases mixed
+    const int zk = (iz <= my / 2) ? 2 * iz : 2 * (iz - my / 2 - 1) + 1;
+#elif defined(MCMCEQ_ORDER_MIDDLE_FIRST)
+    const int zk = 2 * my + 1 - ((iz <= my / 2) ? 2 * iz : 2 * (my - iz) + 1);
+#else
+    const int zk = iz;
+#endif
+    keys[g] = ((uint64_t)zk << 32) | (w << 28) | (d0 << 23) | (u0 << 18) | (d1 << 13) | (u1 << 8) | (d2 << 3);
     vals[g] = g;
 }
 
