@@ -212,6 +212,10 @@ __global__ void eik_key_kernel(EikBatch b, int max_solves, uint64_t* keys, int32
     const int zk = (iz <= my / 2) ? 2 * iz : 2 * (my - iz) + 1;
 #elif defined(MCMCEQ_ORDER_INTERLEAVE)     // upper and lower half of the depth range alternately: long and short box phases mixed
     const int zk = (iz <= my / 2) ? 2 * iz : 2 * (iz - my / 2 - 1) + 1;
+#elif defined(MCMCEQ_ORDER_MID_UP_DOWN)     // from the middle down to the bottom, then from the middle up to the top (two monotone runs)
+    const int zk = (iz > my / 2) ? iz - my / 2 - 1 : my - iz;
+#elif defined(MCMCEQ_ORDER_TOP_BOTTOM_IN)  // from the top to the middle, then from the bottom to the middle
+    const int zk = (iz <= my / 2) ? iz : my / 2 + 1 + (my - iz);
 #elif defined(MCMCEQ_ORDER_MIDDLE_FIRST)
     const int zk = 2 * my + 1 - ((iz <= my / 2) ? 2 * iz : 2 * (my - iz) + 1);
 #else
